@@ -1,0 +1,249 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):   python oracle/make_golden.py
+The reference is a Python tree and cannot travel to the GPU box, so its outputs on seeded
+synthetic inputs are committed as small fixtures; this script is the committed recipe.
+Every fixture stores inputs, weights and the reference's outputs (fp64 = reference modules
+cast with .double(); fp32 = the reference as shipped).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+from _ref_import import import_reference  # noqa: E402
+import pita_oracle as O  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+ref = import_reference()
+
+
+def make_net(n, seed, strong):
+    torch.manual_seed(seed)
+    net = ref.egnn.EGNN_dynamics(n_particles=n, n_dimension=3, hidden_nf=32, n_layers=3,
+                                 act_fn=torch.nn.SiLU(), recurrent=True, tanh=True, attention=True,
+                                 condition_time=True, condition_temperature=True, agg="sum")
+    if strong:  # make the coordinate branch numerically visible (random init has gain 1e-3)
+        with torch.no_grad():
+            for l in range(3):
+                getattr(net.egnn, f"gcl_{l}").coord_mlp[2].weight.mul_(300.0)
+    return net
+
+
+def sd_np(net, prefix):
+    return {prefix + k: v.detach().double().numpy() for k, v in net.state_dict().items()}
+
+
+class FakeTrainer:
+    world_size = 1
+    global_rank = 0
+    num_nodes = 1
+
+
+class FakeLM:
+    trainer = FakeTrainer()
+
+    @staticmethod
+    def all_gather(v):
+        if isinstance(v, dict):
+            return {k: (None if t is None else t.unsqueeze(0)) for k, t in v.items()}
+        return v.unsqueeze(0)
+
+
+class LJTarget:
+    """LennardJonesEnergy.__call__ (lennardjones_energy.py:213-227) around the reference's own
+    LennardJonesPotential; the reference class itself eagerly loads external .npy datasets."""
+    is_molecule = True
+    n_spatial_dim = 3
+
+    def __init__(self, n, temperature=1.0, dtype=torch.float32):
+        self.n_particles = n
+        self.temperature = temperature
+        self.pot = ref.lj.LennardJonesPotential(dim=3 * n, n_particles=n, two_event_dims=False,
+                                                temperature=temperature)
+
+    def __call__(self, samples, return_force=False):
+        with torch.enable_grad():
+            s = samples.detach().clone().requires_grad_(True)
+            lp = self.pot._log_prob(s).squeeze(-1)
+            if return_force:
+                f = torch.autograd.grad(lp.sum(), s)[0]
+                return lp.detach(), f.detach()
+            return lp.detach()
+
+
+def golden_egnn_and_fk():
+    for n, B in ((13, 6), (55, 3)):
+        for strong in (False, True):
+            tag = f"n{n}_{'strong' if strong else 'init'}"
+            net_e = make_net(n, 12345, strong)
+            net_s = make_net(n, 54321 if strong else 12345, strong)
+            gen = torch.Generator().manual_seed(1000 + n)
+            sched = ref.noise.ElucidatingNoiseSchedule(sigma_min=0.05, sigma_max=80, rho=7)
+            t = 0.37 if strong else 0.81
+            x32 = O.md_shaped_coords(B, n, seed=7 + n) * (1.0 + float(sched.h(torch.tensor(t))) ** 0.5 * 0.3)
+            x32 = x32 + 0.3 * torch.randn(B, 3 * n, generator=gen)
+            x32 = ref.data_utils.remove_mean(x32, n, 3)
+            beta = 0.75
+            out = {"n": n, "t": t, "beta": beta, "x": x32.double().numpy(), "sigma_min": 0.05,
+                   "gamma": 4.0 / 3.0}
+            out.update(sd_np(net_e, "E."))
+            out.update(sd_np(net_s, "S."))
+            # raw EGNN forward, fp32 as shipped and fp64
+            tc = torch.linspace(-0.4, 0.9, B)
+            bb = torch.linspace(0.5, 1.5, B)
+            out["egnn_tcond"], out["egnn_beta"] = tc.double().numpy(), bb.double().numpy()
+            out["egnn_out_f32"] = net_s(tc, x32, bb).detach().numpy()
+            for dt_name, dt in (("f64", torch.float64),):
+                torch.set_default_dtype(dt)
+                ne, ns_ = net_e.double(), net_s.double()
+                x = x32.double()
+                out["egnn_out_f64"] = ns_(tc.double(), x, bb.double()).detach().numpy()
+                en = ref.energy_net.EnergyNet(ne)
+                sn = ref.score_net.ScoreNet(ns_)
+                sde = ref.sdes.VEReverseSDE(sched, energy_net=en, score_net=sn, pin_energy=False,
+                                            debias_inference=True,
+                                            cdf=lambda h, xx, b_, _f=sn.forward: ref.utils.compute_divergence_exact(_f, h, xx, b_))
+                sde.trainer = FakeTrainer()
+                gs = ref.anneal.ConstantAnnealingFactorSchedule(4.0 / 3.0)
+                terms = sde.f(torch.tensor(t), x.clone(), torch.tensor(beta), gs, 1.0, None, resampling_interval=1)
+                out["drift_X"] = terms.drift_X.detach().numpy()
+                out["drift_A"] = terms.drift_A.detach().numpy()
+                out["div_b"] = terms.divergence_score.detach().numpy()
+                out["cross"] = terms.cross_term.detach().numpy()
+                out["dUt_dt"] = terms.dUt_dt.detach().numpy()
+                tt = torch.full((B,), t)
+                ht = sched.h(tt)
+                xr = x.clone().requires_grad_(True)
+                out["U"] = en.forward_energy(ht, xr, torch.tensor(beta)).detach().numpy()
+                out["gradU"] = en.forward(ht, xr, torch.tensor(beta)).detach().numpy()
+                out["score"] = sn.forward(ht, x, torch.tensor(beta)).detach().numpy()
+                out["div_score"] = ref.utils.compute_divergence_exact(sn.forward, ht, x, torch.tensor(beta)).numpy()
+                # not-debiased branch (sdes.py:117-128)
+                sde_nd = ref.sdes.VEReverseSDE(sched, energy_net=en, score_net=sn, debias_inference=False,
+                                               cdf=lambda *a: None)
+                out["drift_X_nodebias"] = sde_nd.f(torch.tensor(t), x.clone(), torch.tensor(beta), gs, 1.0,
+                                                   None).drift_X.detach().numpy()
+                torch.set_default_dtype(torch.float32)
+            np.savez_compressed(os.path.join(OUT, f"fk_{tag}.npz"), **out)
+            print("wrote fk_%s" % tag, "drift_A", out["drift_A"][:3])
+
+
+def golden_resample():
+    out = {}
+    cases = [(16, 1, 3.0), (1000, 2, 3.0), (4096, 3, 0.5), (65536, 4, 3.0), (1 << 18, 5, 3.0)]
+    for N, seed, scale in cases:
+        g = torch.Generator().manual_seed(seed)
+        logits = torch.randn(N, generator=g) * scale
+        torch.manual_seed(100 + seed)
+        u0 = float(torch.rand(size=(1,), dtype=torch.float64))
+        torch.manual_seed(100 + seed)
+        ids, _ = ref.utils.sample_cat_sys(N, logits)
+        w = torch.clip(torch.softmax(logits, dim=-1), 1e-6, 1.0)
+        # claim used by the oracle: torch CPU cumsum(fp32) == fp32(cumsum in fp64)
+        bins_t = torch.cumsum(w, dim=-1).numpy()
+        bins_n = np.cumsum(w.numpy().astype(np.float64)).astype(np.float32)
+        out[f"cumsum_claim_{N}"] = np.array(int(np.array_equal(bins_t, bins_n)))
+        if N <= 65536:
+            out[f"logits_{N}"] = logits.numpy()
+        out[f"weights_{N}"] = w.numpy()
+        out[f"u0_{N}"] = np.array(u0)
+        if N <= 65536:
+            out[f"ids_{N}"] = ids.astype(np.int32)
+        else:  # keep the fixture small: strided sample + run-length summary
+            out[f"ids_{N}_stride64"] = ids[::64].astype(np.int32)
+            out[f"ids_{N}_sum"] = np.array(int(ids.sum()))
+            out[f"ids_{N}_unique"] = np.array(len(np.unique(ids)))
+        print("resample N=%d u0=%.6f cumsum-claim=%s unique=%d sumw=%.4f" % (
+            N, u0, bool(out[f"cumsum_claim_{N}"]), len(np.unique(ids)), float(w.double().sum())))
+    # edge-case offsets
+    g = torch.Generator().manual_seed(9)
+    logits = torch.randn(257, generator=g) * 2
+    w = torch.clip(torch.softmax(logits, dim=-1), 1e-6, 1.0)
+    for name, u0 in (("zero", 0.0), ("almost1", 1.0 - 2.0 ** -53), ("half", 0.5)):
+        u = (torch.tensor([u0], dtype=torch.float64) + 1 / 257 * torch.arange(257)) % 1.0
+        bins = torch.cumsum(w, dim=-1)
+        ids = np.digitize(u, bins.cpu(), right=True)
+        ids[ids == 257] = 256
+        out[f"edge_{name}_ids"] = ids.astype(np.int32)
+    out["edge_logits"] = logits.numpy()
+    out["case_sizes"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(OUT, "resample.npz"), **out)
+
+
+def golden_lj():
+    out = {}
+    for n, B in ((13, 64), (55, 16)):
+        x = O.md_shaped_coords(B, n, seed=21 + n)
+        for T in (1.0, 2.5):
+            tgt = LJTarget(n, temperature=T)
+            lp, f = tgt(x, return_force=True)
+            pot64 = ref.lj.LennardJonesPotential(dim=3 * n, n_particles=n, two_event_dims=False, temperature=T)
+            xd = x.double().requires_grad_(True)
+            lp64 = pot64._log_prob(xd).squeeze(-1)
+            f64 = torch.autograd.grad(lp64.sum(), xd)[0]
+            out[f"x_{n}"] = x.numpy()
+            out[f"logp_f32_{n}_T{T}"], out[f"force_f32_{n}_T{T}"] = lp.numpy(), f.numpy()
+            out[f"logp_f64_{n}_T{T}"], out[f"force_f64_{n}_T{T}"] = lp64.detach().numpy(), f64.numpy()
+        # in-repo independent restatement energy2 (sampling/sample_lj13.py:24-30), eps-free
+        v = x.double().reshape(B, n, 3)
+        d = torch.vmap(torch.pdist)(v)
+        e2 = 2 * ((1 / d) ** 12 - 2 * (1 / d) ** 6).sum(-1) + 0.5 * (v - v.mean(1, keepdim=True)).pow(2).sum((-2, -1))
+        out[f"energy2_neg_{n}"] = (-e2).numpy()
+    np.savez_compressed(os.path.join(OUT, "lj.npz"), **out)
+    print("wrote lj")
+
+
+def golden_loop():
+    """integrate_sde end to end (sde_integration.py:98-212), fp64 default dtype for a tight pin."""
+    n, N, S, chunk = 13, 32, 6, 16
+    torch.set_default_dtype(torch.float64)
+    try:
+        net_e = make_net(n, 12345, True).double()
+        net_s = make_net(n, 54321, True).double()
+        sched = ref.noise.ElucidatingNoiseSchedule(sigma_min=0.05, sigma_max=80, rho=7)
+        en, sn = ref.energy_net.EnergyNet(net_e), ref.score_net.ScoreNet(net_s)
+        sde = ref.sdes.VEReverseSDE(sched, energy_net=en, score_net=sn, pin_energy=False, debias_inference=True,
+                                    cdf=lambda h, xx, b_, _f=sn.forward: ref.utils.compute_divergence_exact(_f, h, xx, b_))
+        sde.trainer = FakeTrainer()
+        gam = 4.0 / 3.0
+        integ = ref.integ.WeightedSDEIntegrator(
+            sde=sde, num_integration_steps=S, start_resampling_step=1, end_resampling_step=5,
+            lightning_module=FakeLM(), partial_annealing_factor_schedule=None, resampling_interval=1,
+            num_negative_time_steps=0, post_mcmc_steps=0, batch_size=chunk, resample_at_end=True,
+            diffusion_scale=1.0)
+        tgt = LJTarget(n, temperature=1.0)
+        torch.manual_seed(2024)
+        scale = float((sched.h(torch.tensor(1.0)) / gam) ** 0.5)
+        x1 = ref.prior.Prior(scale, n_particles=n, spatial_dim=3).sample(N)
+        x1_in = x1.clone()
+        x, logw, uniq, terms, acc = integ.integrate_sde(
+            x1, tgt, ref.anneal.ConstantAnnealingFactorSchedule(gam), inverse_temperature=torch.tensor(0.75))
+        out = {"n": n, "N": N, "S": S, "chunk": chunk, "seed": 2024, "gamma": gam, "beta": 0.75,
+               "x1": x1_in.detach().numpy(), "x_final": x.detach().numpy(), "logweights": logw.detach().numpy(),
+               "num_unique": np.array(uniq), "prior_scale": scale,
+               "drift_A_step0": terms[0].drift_A.numpy()}
+        out.update(sd_np(net_e, "E."))
+        out.update(sd_np(net_s, "S."))
+        np.savez_compressed(os.path.join(OUT, "loop_n13.npz"), **out)
+        print("wrote loop", uniq)
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ["resample", "lj", "fk", "loop"]
+    if "resample" in which:
+        golden_resample()
+    if "lj" in which:
+        golden_lj()
+    if "fk" in which:
+        golden_egnn_and_fk()
+    if "loop" in which:
+        golden_loop()
