@@ -136,7 +136,7 @@ def golden_egnn_and_fk():
 
 def golden_resample():
     out = {}
-    cases = [(16, 1, 3.0), (1000, 2, 3.0), (4096, 3, 0.5), (65536, 4, 3.0), (1 << 18, 5, 3.0)]
+    cases = [(16, 1, 3.0), (1000, 2, 3.0), (4096, 3, 0.5), (65536, 4, 3.0), (100003, 6, 2.0), (1 << 18, 5, 3.0)]
     for N, seed, scale in cases:
         g = torch.Generator().manual_seed(seed)
         logits = torch.randn(N, generator=g) * scale

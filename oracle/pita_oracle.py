@@ -323,7 +323,10 @@ def systematic_indices(weights32: np.ndarray, u0: float) -> np.ndarray:
     w = np.asarray(weights32, dtype=np.float32)
     N = w.shape[0]
     bins = np.cumsum(w.astype(np.float64)).astype(np.float32)
-    u = (np.float64(u0) + (1.0 / N) * np.arange(N, dtype=np.float64)) % 1.0
+    # `1 / bs * torch.arange(bs)` is evaluated in float32 (python float x int64 tensor -> default
+    # dtype) before the float64 add (utils.py:113): the grid is fl32(fl32(1/N) * fl32(i)).
+    grid = (np.float32(1.0 / N) * np.arange(N).astype(np.float32)).astype(np.float64)
+    u = (np.float64(u0) + grid) % 1.0
     ids = np.searchsorted(bins.astype(np.float64), u, side="left")
     ids[ids == N] = N - 1
     return ids.astype(np.int64)

@@ -1,0 +1,129 @@
+"""EGNN kernels (forward, energy reverse pass, score + exact divergence) vs the reference's golden outputs
+and the fp64 autograd oracle, through the C-ABI.  Tolerance: 1e-4 relative (north star), fp32 kernels."""
+import numpy as np
+import pytest
+import torch
+
+import pita_oracle as O
+from helpers import assert_close, golden, make_net, state_from_golden
+
+pytestmark = pytest.mark.gpu
+
+FK_CASES = ["fk_n13_init.npz", "fk_n13_strong.npz", "fk_n55_init.npz", "fk_n55_strong.npz"]
+
+
+@pytest.mark.parametrize("name", FK_CASES)
+def test_forward_vs_reference_golden(name):
+    g = golden(name)
+    n = int(g["n"])
+    net = make_net(n, state_from_golden(g, "S."))
+    x = torch.from_numpy(g["x"]).float().cuda()
+    out = net(torch.from_numpy(g["egnn_tcond"]).float().cuda(), x, torch.from_numpy(g["egnn_beta"]).float().cuda())
+    assert_close(out, g["egnn_out_f64"], "EGNN_dynamics.forward vs reference fp64")
+
+
+@pytest.mark.parametrize("name", FK_CASES)
+def test_energy_score_divergence_vs_reference_golden(name):
+    from pita_b200.energy_net import EnergyNet
+    from pita_b200.noise_schedules import ElucidatingNoiseSchedule
+    from pita_b200.score_net import ScoreNet
+    g = golden(name)
+    n, t, beta = int(g["n"]), float(g["t"]), float(g["beta"])
+    en = EnergyNet(make_net(n, state_from_golden(g, "E.")))
+    sn = ScoreNet(make_net(n, state_from_golden(g, "S.")))
+    x = torch.from_numpy(g["x"]).float().cuda()
+    sched = ElucidatingNoiseSchedule(float(g["sigma_min"]), 80.0, 7.0)
+    B = x.shape[0]
+    ht = torch.full((B,), float(sched.h(torch.tensor(t, dtype=torch.float64))), device="cuda")
+    U, gU, dh = en._terms(ht, x, beta, True, True)
+    assert_close(U, g["U"], "forward_energy")
+    assert_close(gU, g["gradU"], "grad_x U")
+    dh_dt = float(sched.dh_dt(torch.tensor(t, dtype=torch.float64)))
+    assert_close(dh * dh_dt, g["dUt_dt"], "dU/dt")
+    s, div = sn.score_and_divergence(ht, x, beta)
+    assert_close(s, g["score"], "score")
+    assert_close(div, g["div_score"], "div score")
+    assert_close(en.forward_energy(ht, x, beta), g["U"], "forward_energy (energy-only launch)")
+    assert_close(sn.forward(ht, x, beta), g["score"], "score (no divergence launch)")
+
+
+@pytest.mark.parametrize("name", FK_CASES)
+def test_sde_f_terms_vs_reference_golden(name):
+    """VEReverseSDE.f through the drop-in classes == reference SDETerms (sdes.py:130-239)."""
+    from pita_b200.annealing_factor_schedules import ConstantAnnealingFactorSchedule
+    from pita_b200.energy_net import EnergyNet
+    from pita_b200.noise_schedules import ElucidatingNoiseSchedule
+    from pita_b200.score_net import ScoreNet
+    from pita_b200.sdes import VEReverseSDE
+    g = golden(name)
+    n, t, beta = int(g["n"]), float(g["t"]), float(g["beta"])
+    sde = VEReverseSDE(ElucidatingNoiseSchedule(float(g["sigma_min"]), 80.0, 7.0),
+                       energy_net=EnergyNet(make_net(n, state_from_golden(g, "E."))),
+                       score_net=ScoreNet(make_net(n, state_from_golden(g, "S."))))
+    x = torch.from_numpy(g["x"]).float().cuda()
+    terms = sde.f(torch.tensor(t), x, torch.tensor(beta), ConstantAnnealingFactorSchedule(float(g["gamma"])), 1.0, None,
+                  resampling_interval=1)
+    assert_close(terms.drift_X, g["drift_X"], "drift_X")
+    assert_close(terms.divergence_score, g["div_b"], "div_b")
+    assert_close(terms.cross_term, g["cross"], "cross_term")
+    assert_close(terms.dUt_dt, g["dUt_dt"], "dUt_dt")
+    assert_close(terms.drift_A, g["drift_A"], "drift_A")
+    sde.debias_inference = False
+    nd = sde.f(torch.tensor(t), x, torch.tensor(beta), ConstantAnnealingFactorSchedule(float(g["gamma"])), 1.0, None)
+    assert_close(nd.drift_X, g["drift_X_nodebias"], "drift_X (not debiased)")
+
+
+@pytest.mark.parametrize("n,B", [(13, 37), (55, 5)])
+@pytest.mark.parametrize("gain", [0.001, 0.3])
+def test_kernels_vs_fp64_oracle_random(n, B, gain):
+    """Seeded random weights / MD-shaped inputs / per-particle noise levels vs the fp64 autograd oracle."""
+    from pita_b200 import ops
+    from pita_b200.egnn_temp_conditioned import pack_state_dict
+    sdE = O.random_egnn_state(seed=100 + n, dtype=torch.float64, coord_gain=gain)
+    sdS = O.random_egnn_state(seed=200 + n, dtype=torch.float64, coord_gain=gain)
+    sched = O.EDMSchedule(0.05)
+    t = torch.linspace(0.05, 0.98, B, dtype=torch.float64)
+    ht = sched.h(t)
+    x = O.md_shaped_coords(B, n, seed=n, dtype=torch.float64) * (1 + ht.sqrt()[:, None] * 0.5)
+    x = O.centre(x, n)
+    beta = 1.3
+    tr, xr = t.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    E = O.model_energy(sdE, sched.h(tr), xr, beta, n)
+    gx, gt = torch.autograd.grad(E.sum(), (xr, tr))
+    s_ref = O.model_score(sdS, ht, x, beta, n)
+    div_ref = O.exact_divergence(lambda h1, x1: O.model_score(sdS, h1, x1, beta, n), ht, x)
+    wE, wS = pack_state_dict(sdE, 32, 3, "cuda"), pack_state_dict(sdS, 32, 3, "cuda")
+    e, g, dh = ops.egnn_energy(wE, 32, 3, n, ht.float().cuda(), x.float().cuda(), beta)
+    assert_close(e, E, "E")
+    assert_close(g, gx, "grad E")
+    assert_close(dh.double().cpu() * sched.dh_dt(t), gt, "dE/dt")
+    s, d = ops.egnn_score_div(wS, 32, 3, n, ht.float().cuda(), x.float().cuda(), beta)
+    assert_close(s, s_ref, "score")
+    assert_close(d, div_ref, "div")
+
+
+@pytest.mark.parametrize("n", [13, 55])
+def test_full_size_properties(n):
+    """Properties that hold at any size, checked at a size the oracle could not finish:
+    determinism, permutation of the batch, rigid translation (score/energy-gradient are translation covariant
+    only through the explicit x terms), batch-slice consistency with a small oracle-checked slice."""
+    from pita_b200 import ops
+    from pita_b200.egnn_temp_conditioned import pack_state_dict
+    B = 2048 if n == 13 else 296
+    sd = O.random_egnn_state(seed=7, dtype=torch.float64, coord_gain=0.3)
+    w = pack_state_dict(sd, 32, 3, "cuda")
+    sched = O.EDMSchedule(0.05)
+    ht = torch.full((B,), float(sched.h(torch.tensor(0.4, dtype=torch.float64))))
+    x = O.centre(O.md_shaped_coords(B, n, seed=3) * 1.5, n)
+    s1, d1 = ops.egnn_score_div(w, 32, 3, n, ht.cuda(), x.cuda(), 1.0)
+    s2, d2 = ops.egnn_score_div(w, 32, 3, n, ht.cuda(), x.cuda(), 1.0)
+    assert torch.equal(s1, s2) and torch.equal(d1, d2), "not deterministic"
+    perm = torch.randperm(B)
+    s3, d3 = ops.egnn_score_div(w, 32, 3, n, ht.cuda(), x[perm].cuda(), 1.0)
+    assert torch.equal(s3.cpu(), s1.cpu()[perm]) and torch.equal(d3.cpu(), d1.cpu()[perm]), "batch order dependence"
+    e1, g1, h1 = ops.egnn_energy(w, 32, 3, n, ht.cuda(), x.cuda(), 1.0)
+    e2, g2, h2 = ops.egnn_energy(w, 32, 3, n, ht.cuda(), x.cuda(), 1.0)
+    assert torch.equal(e1, e2) and torch.equal(g1, g2) and torch.equal(h1, h2), "reverse pass not deterministic"
+    k = 3
+    div_ref = O.exact_divergence(lambda hh, xx: O.model_score(sd, hh, xx, 1.0, n), ht[:k].double(), x[:k].double())
+    assert_close(d1[:k], div_ref, "div slice")

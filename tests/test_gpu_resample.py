@@ -1,0 +1,110 @@
+"""Systematic resampler: indices bit-exact vs the reference (golden) and the oracle, through the C-ABI."""
+import numpy as np
+import pytest
+import torch
+
+import pita_oracle as O
+from helpers import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _ids(w, u0, lo=0, hi=None):
+    from pita_b200 import ops
+    ids, ch = ops.resample_systematic(torch.as_tensor(w).cuda(), u0, lo, hi)
+    return ids.cpu().numpy(), int(ch.item())
+
+
+def test_indices_bit_exact_vs_reference_golden():
+    g = golden("resample.npz")
+    for N in g["case_sizes"]:
+        N = int(N)
+        ids, ch = _ids(g[f"weights_{N}"], float(g[f"u0_{N}"]))
+        if f"ids_{N}" in g.files:
+            ref = g[f"ids_{N}"].astype(np.int64)
+            assert np.array_equal(ids, ref), f"N={N}: {(ids != ref).sum()} mismatches"
+            assert max(ch, 1) == len(np.unique(ref))
+        else:
+            assert np.array_equal(ids[::64], g[f"ids_{N}_stride64"].astype(np.int64))
+            assert int(ids.sum()) == int(g[f"ids_{N}_sum"])
+            assert max(ch, 1) == int(g[f"ids_{N}_unique"])
+
+
+def test_edge_offsets_vs_reference_golden():
+    g = golden("resample.npz")
+    w = O.clipped_softmax(torch.from_numpy(g["edge_logits"])).numpy()
+    for name, u0 in (("zero", 0.0), ("almost1", 1.0 - 2.0 ** -53), ("half", 0.5)):
+        ids, _ = _ids(w, u0)
+        assert np.array_equal(ids, g[f"edge_{name}_ids"].astype(np.int64)), name
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 2049, 100003, 1 << 20, (1 << 22) + 5])
+def test_indices_bit_exact_vs_oracle_given_weights(N):
+    gen = torch.Generator().manual_seed(N)
+    logits = torch.randn(N, generator=gen) * 3.0
+    w = O.clipped_softmax(logits).numpy()
+    for u0 in (0.0, 0.123456789, 0.999999):
+        ids, ch = _ids(w, u0)
+        ref = O.systematic_indices(w, u0)
+        assert np.array_equal(ids, ref), f"N={N} u0={u0}: {(ids != ref).sum()} mismatches"
+        assert max(ch, 1) == len(np.unique(ref))
+
+
+def test_degenerate_weights():
+    N = 4096
+    w = np.full(N, 1e-6, dtype=np.float32)
+    w[17] = 1.0
+    ids, ch = _ids(w, 0.3)
+    assert np.array_equal(ids, O.systematic_indices(w, 0.3))
+    w2 = np.full(N, 1.0 / N, dtype=np.float32)  # uniform: identity up to rotation
+    ids2, ch2 = _ids(w2, 0.0)
+    assert np.array_equal(ids2, O.systematic_indices(w2, 0.0))
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_slot_ranges_concatenate_to_full(world):
+    N = 1 << 16
+    gen = torch.Generator().manual_seed(3)
+    w = O.clipped_softmax(torch.randn(N, generator=gen) * 2).numpy()
+    full, ch_full = _ids(w, 0.77)
+    parts, ch = [], 0
+    for r in range(world):
+        p, c = _ids(w, 0.77, r * N // world, (r + 1) * N // world)
+        parts.append(p)
+        ch += c
+    assert np.array_equal(np.concatenate(parts), full)
+    assert ch == ch_full == len(np.unique(full))
+
+
+@pytest.mark.parametrize("N", [1000, 1 << 20])
+def test_softmax_clip_close_to_torch(N):
+    from pita_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    logits = torch.randn(N, generator=gen) * 3.0
+    w = ops.softmax_clip(logits.cuda()).cpu()
+    ref = O.clipped_softmax(logits.double()).float()
+    rel = ((w - ref).abs() / ref).max().item()
+    assert rel < 2e-6, rel
+    # indices from logits: identical up to a vanishing fraction of boundary flips
+    from pita_b200.utils import sample_cat_sys
+    ids, _ = sample_cat_sys(N, logits.cuda(), u0=0.4321)
+    ref_ids = O.systematic_resample(logits, 0.4321)
+    assert (ids.cpu().numpy() != ref_ids).mean() < 1e-3
+
+
+@pytest.mark.parametrize("D", [39, 165])
+def test_gather_rows_and_remove_mean(D):
+    from pita_b200 import ops
+    N = 5000
+    x = torch.randn(N, D, device="cuda")
+    ids = torch.randint(0, N, (N,), device="cuda")
+    out = ops.gather_rows([x.data_ptr()], N, ids, D)
+    assert torch.equal(out, x[ids])
+    # multi-"rank" base pointers (two halves of the same allocation)
+    half = N // 2
+    out2 = ops.gather_rows([x.data_ptr(), x[half:].data_ptr()], half, ids, D)
+    assert torch.equal(out2, x[ids])
+    n = D // 3
+    got = ops.remove_mean(x, n)
+    ref = O.centre(x.cpu().double(), n)
+    assert (got.cpu().double() - ref).abs().max().item() < 1e-6

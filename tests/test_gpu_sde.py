@@ -1,0 +1,140 @@
+"""Fused SDE/FK step, chunk-quantile clamp and the whole annealed loop vs the oracle (through the C-ABI)."""
+import numpy as np
+import pytest
+import torch
+
+import pita_oracle as O
+from helpers import assert_close, golden, make_net, state_from_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,B", [(13, 1000), (55, 333)])
+@pytest.mark.parametrize("debias", [True, False])
+def test_fused_step_vs_formula(n, B, debias):
+    from pita_b200 import ops
+    D = 3 * n
+    gen = torch.Generator().manual_seed(B)
+    x, gu, sc, nz = (torch.randn(B, D, generator=gen, dtype=torch.float64) for _ in range(4))
+    div, dEdh, en = (torch.randn(B, generator=gen, dtype=torch.float64) for _ in range(3))
+    p = dict(g2=3.7, gamma=1.3333, dgamma_dt=0.21, dh_dt=5.5, dt=0.01, sqrt_dt=0.1, noise_scale=1.9)
+    if debias:
+        bt = sc * p["g2"] / 2
+        dX = p["gamma"] * (-gu) * p["g2"] / 2 + p["gamma"] * bt
+        raw = p["gamma"] ** 2 * (-gu * bt).sum(-1) + p["gamma"] * div * p["g2"] / 2 + p["gamma"] * dEdh * p["dh_dt"] + p["dgamma_dt"] * en
+    else:
+        dX = p["gamma"] * sc * p["g2"]
+        raw = None
+    ref = O.centre(x + dX * p["dt"] + p["noise_scale"] * nz * p["sqrt_dt"], n)
+    c = lambda v: v.float().cuda()  # noqa: E731
+    xo, a_raw = ops.sde_fk_step(c(x), c(gu), c(sc), c(nz), c(div), c(dEdh), c(en), n, debias=debias, want_a_raw=debias, **p)
+    assert_close(xo, ref, "x_next", rtol=1e-5)
+    if debias:
+        assert_close(a_raw, raw, "a_raw", rtol=1e-5)
+    # frozen step: x_out = remove_mean(x)
+    xf, _ = ops.sde_fk_step(c(x), None, None, None, None, None, None, n, debias=False, freeze_x=True, want_a_raw=False, **p)
+    assert_close(xf, O.centre(x, n), "frozen x", rtol=1e-6)
+    # in-kernel Philox noise: unit variance, zero mean, reproducible, different per offset
+    z = torch.zeros(B, D, device="cuda")
+    q = dict(p, noise_scale=1.0, sqrt_dt=1.0)
+    n1, _ = ops.sde_fk_step(z, z, z, None, None, None, None, n, debias=False, remove_mean=False, seed=5, offset=1, want_a_raw=False, **q)
+    n2, _ = ops.sde_fk_step(z, z, z, None, None, None, None, n, debias=False, remove_mean=False, seed=5, offset=1, want_a_raw=False, **q)
+    n3, _ = ops.sde_fk_step(z, z, z, None, None, None, None, n, debias=False, remove_mean=False, seed=5, offset=2, want_a_raw=False, **q)
+    assert torch.equal(n1, n2) and not torch.equal(n1, n3)
+    assert abs(n1.mean().item()) < 0.02 and abs(n1.std().item() - 1.0) < 0.02
+
+
+@pytest.mark.parametrize("B,chunk", [(512, 512), (1000, 128), (5000, 512), (37, 512), (8192, 8192), (1, 16)])
+def test_quantile_clamp_vs_torch(B, chunk):
+    from pita_b200 import ops
+    gen = torch.Generator().manual_seed(B + chunk)
+    raw = torch.randn(B, generator=gen) * 10
+    a = torch.randn(B, generator=gen)
+    a_out, drift = ops.fk_quantile_accumulate(raw.cuda(), a.cuda(), chunk, 0.9, 0.01, False, want_drift=True)
+    ref = torch.cat([O.quantile_clamp(raw[lo:lo + chunk]) for lo in range(0, B, chunk)])
+    assert torch.equal(drift.cpu(), ref), (drift.cpu() - ref).abs().max()
+    assert_close(a_out, a.double() + ref.double() * 0.01, "a_next", rtol=1e-6)
+    z, _ = ops.fk_quantile_accumulate(raw.cuda(), a.cuda(), chunk, 0.9, 0.01, True)
+    assert z.abs().max().item() == 0.0
+    only, _ = ops.fk_quantile_accumulate(raw.cuda(), None, chunk, 0.9, 0.0, False)
+    assert torch.equal(only.cpu(), ref)
+
+
+def _build_integrator(n, sdE, sdS, S, chunk, **kw):
+    from pita_b200.energy_net import EnergyNet
+    from pita_b200.noise_schedules import ElucidatingNoiseSchedule
+    from pita_b200.score_net import ScoreNet
+    from pita_b200.sde_integration import WeightedSDEIntegrator
+    from pita_b200.sdes import VEReverseSDE
+    sde = VEReverseSDE(ElucidatingNoiseSchedule(0.05, 80.0, 7.0), energy_net=EnergyNet(make_net(n, sdE)),
+                       score_net=ScoreNet(make_net(n, sdS)), debias_inference=kw.pop("debias", True))
+    return WeightedSDEIntegrator(sde=sde, num_integration_steps=S, lightning_module=None, batch_size=chunk,
+                                 num_negative_time_steps=0, post_mcmc_steps=0, **kw)
+
+
+def test_loop_vs_reference_golden():
+    """integrate_sde end to end on the reference's own trajectory fixture (fp64 reference, fp32 kernels):
+    the same noise / offsets are injected; ancestors must match exactly and x / log-weights to 1e-4."""
+    from pita_b200.annealing_factor_schedules import ConstantAnnealingFactorSchedule
+    from pita_b200.lennardjones_energy import LennardJonesEnergy
+    g = golden("loop_n13.npz")
+    n, N, S, chunk = int(g["n"]), int(g["N"]), int(g["S"]), int(g["chunk"])
+    sdE, sdS = state_from_golden(g, "E."), state_from_golden(g, "S.")
+    # replay the reference's random stream on the CPU generator (prior, per-chunk noise, u0)
+    torch.manual_seed(int(g["seed"]))
+    x1 = O.mean_free_prior(N, n, float(g["prior_scale"]), dtype=torch.float64)
+    noises, u0s = {}, {}
+    cfg = O.LoopConfig(n=n, steps=S, chunk=chunk, beta=float(g["beta"]), resampling_interval=1, start_resampling_step=1,
+                       end_resampling_step=5, resample_at_end=True)
+
+    def noise_fn(step, xc):
+        z = torch.randn_like(xc)
+        noises.setdefault(step, []).append(z)
+        return z
+
+    def u0_fn(step):
+        u0s[step] = float(torch.rand(size=(1,), dtype=torch.float64))
+        return u0s[step]
+
+    x_ref, logw_ref, uniq_ref = O.integrate(sdE, sdS, O.EDMSchedule(0.05), O.ConstGamma(float(g["gamma"])), cfg, x1, noise_fn, u0_fn)
+    assert list(uniq_ref) == list(g["num_unique"])  # the oracle replays the reference
+    integ = _build_integrator(n, sdE, sdS, S, chunk, start_resampling_step=1, end_resampling_step=5, resampling_interval=1,
+                              resample_at_end=True)
+    integ.noise_fn = lambda step, x: torch.cat(noises[step]).float().cuda()
+    integ.u0_fn = lambda step: u0s[step]
+    tgt = LennardJonesEnergy(dimensionality=3 * n, n_particles=n, temperature=1.0)
+    x, logw, uniq, terms, acc = integ.integrate_sde(x1.float().cuda(), tgt, ConstantAnnealingFactorSchedule(float(g["gamma"])),
+                                                    inverse_temperature=float(g["beta"]))
+    assert list(uniq) == list(g["num_unique"]), (uniq, list(g["num_unique"]))
+    assert_close(logw, g["logweights"], "logweights vs reference", rtol=2e-4)
+    assert_close(x, g["x_final"], "x_final vs reference", rtol=2e-4)
+
+
+@pytest.mark.parametrize("n,N,S,chunk", [(13, 96, 4, 32), (55, 12, 3, 6), (13, 50, 3, 16)])
+def test_loop_vs_oracle(n, N, S, chunk):
+    from pita_b200.annealing_factor_schedules import ConstantAnnealingFactorSchedule
+    from pita_b200.lennardjones_energy import LennardJonesEnergy
+    sdE = O.random_egnn_state(seed=31 + n, dtype=torch.float64, coord_gain=0.3)
+    sdS = O.random_egnn_state(seed=32 + n, dtype=torch.float64, coord_gain=0.3)
+    gam = 4.0 / 3.0
+    sched = O.EDMSchedule(0.05)
+    gen = torch.Generator().manual_seed(N)
+    x1 = O.mean_free_prior(N, n, float((sched.h(torch.tensor(1.0)) / gam) ** 0.5), gen=gen, dtype=torch.float64)
+    noise = {s: torch.randn(N, 3 * n, generator=gen, dtype=torch.float64) for s in range(S)}
+    u0 = {s: float(torch.rand(1, generator=gen, dtype=torch.float64)) for s in range(S + 1)}
+    cfg = O.LoopConfig(n=n, steps=S, chunk=chunk, beta=0.9, resampling_interval=1)
+    cursor = {}
+
+    def noise_fn(step, xc):
+        lo = cursor.get(step, 0)
+        cursor[step] = lo + xc.shape[0]
+        return noise[step][lo:lo + xc.shape[0]]
+
+    x_ref, logw_ref, uniq_ref = O.integrate(sdE, sdS, sched, O.ConstGamma(gam), cfg, x1, noise_fn, lambda s: u0[s])
+    integ = _build_integrator(n, sdE, sdS, S, chunk, start_resampling_step=0, end_resampling_step=10 ** 9, resampling_interval=1)
+    integ.noise_fn = lambda step, x: noise[step].float().cuda()
+    integ.u0_fn = lambda step: u0[step]
+    tgt = LennardJonesEnergy(dimensionality=3 * n, n_particles=n)
+    x, logw, uniq, _, _ = integ.integrate_sde(x1.float().cuda(), tgt, ConstantAnnealingFactorSchedule(gam), inverse_temperature=0.9)
+    assert list(uniq) == list(uniq_ref)
+    assert_close(x, x_ref, "x_final", rtol=2e-4)
