@@ -200,8 +200,10 @@ def golden_lj():
 
 
 def golden_loop():
-    """integrate_sde end to end (sde_integration.py:98-212), fp64 default dtype for a tight pin."""
-    n, N, S, chunk = 13, 32, 6, 16
+    """integrate_sde end to end (sde_integration.py:98-212), fp64 default dtype for a tight pin.  S=40 steps keep
+    the explicit Euler step inside its stability region (dt * dlog h/dt < 1), so fp32 and fp64 runs stay comparable;
+    the state after every step is recorded (by wrapping the reference's own step method) for teacher-forced checks."""
+    n, N, S, chunk = 13, 32, 40, 16
     torch.set_default_dtype(torch.float64)
     try:
         net_e = make_net(n, 12345, True).double()
@@ -213,10 +215,19 @@ def golden_loop():
         sde.trainer = FakeTrainer()
         gam = 4.0 / 3.0
         integ = ref.integ.WeightedSDEIntegrator(
-            sde=sde, num_integration_steps=S, start_resampling_step=1, end_resampling_step=5,
-            lightning_module=FakeLM(), partial_annealing_factor_schedule=None, resampling_interval=1,
+            sde=sde, num_integration_steps=S, start_resampling_step=2, end_resampling_step=36,
+            lightning_module=FakeLM(), partial_annealing_factor_schedule=None, resampling_interval=2,
             num_negative_time_steps=0, post_mcmc_steps=0, batch_size=chunk, resample_at_end=True,
             diffusion_scale=1.0)
+        states = []
+        inner = integ.ddp_batched_euler_maruyama_step
+
+        def recording_step(t, x, a, dt, step, **kw):
+            out = inner(t, x, a, dt, step, **kw)
+            states.append((ref.data_utils.remove_mean(out[0], n, 3).detach().clone(), out[1].detach().clone()))
+            return out
+
+        integ.ddp_batched_euler_maruyama_step = recording_step
         tgt = LJTarget(n, temperature=1.0)
         torch.manual_seed(2024)
         scale = float((sched.h(torch.tensor(1.0)) / gam) ** 0.5)
@@ -225,9 +236,11 @@ def golden_loop():
         x, logw, uniq, terms, acc = integ.integrate_sde(
             x1, tgt, ref.anneal.ConstantAnnealingFactorSchedule(gam), inverse_temperature=torch.tensor(0.75))
         out = {"n": n, "N": N, "S": S, "chunk": chunk, "seed": 2024, "gamma": gam, "beta": 0.75,
+               "start": 2, "end": 36, "interval": 2,
                "x1": x1_in.detach().numpy(), "x_final": x.detach().numpy(), "logweights": logw.detach().numpy(),
                "num_unique": np.array(uniq), "prior_scale": scale,
-               "drift_A_step0": terms[0].drift_A.numpy()}
+               "x_steps": torch.stack([s_[0] for s_ in states]).numpy().astype(np.float32),
+               "a_steps": torch.stack([s_[1] for s_ in states]).numpy()}
         out.update(sd_np(net_e, "E."))
         out.update(sd_np(net_s, "S."))
         np.savez_compressed(os.path.join(OUT, "loop_n13.npz"), **out)

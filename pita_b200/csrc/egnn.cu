@@ -923,8 +923,8 @@ static int launch_score(const float *w, const float *ht, const float *x, const f
 }
 
 static int check_common(const char *what, const float *w, int hidden, int layers, int n, const void *a, const void *b_, const void *c, int64_t B) {
-  PITA_REQUIRE(w && a && b_ && c, PITA_EINVAL, "%s: null pointer", what);
   PITA_REQUIRE(B >= 0, PITA_EINVAL, "%s: negative batch", what);
+  PITA_REQUIRE(B == 0 || (w && a && b_ && c), PITA_EINVAL, "%s: null pointer", what);
   if (hidden != 32 || layers != 3) { set_error("%s: only hidden_nf=32, n_layers=3 (configs/model/net/egnn_temp.yaml) is built; got %d/%d", what, hidden, layers); return PITA_EUNSUP; }
   if (n != 13 && n != 55) { set_error("%s: n_particles=%d unsupported (13 or 55)", what, n); return PITA_EUNSUP; }
   return PITA_OK;
@@ -943,8 +943,8 @@ extern "C" int pita_egnn_forward(const float *wpack, int hidden, int layers, int
                                  const float *beta, int64_t B, float *vel, void *stream) {
   int rc = check_common("egnn_forward", wpack, hidden, layers, n, tcond, y, beta, B);
   if (rc) return rc;
-  PITA_REQUIRE(vel, PITA_EINVAL, "egnn_forward: null output");
   if (B == 0) return PITA_OK;
+  PITA_REQUIRE(vel, PITA_EINVAL, "egnn_forward: null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return n == 13 ? launch_forward<13, 13>(wpack, tcond, y, beta, B, vel, s) : launch_forward<55, 11>(wpack, tcond, y, beta, B, vel, s);
 }
@@ -953,8 +953,8 @@ extern "C" int pita_egnn_energy(const float *wpack, int hidden, int layers, int 
                                 const float *beta, int64_t B, float *energy, float *grad_x, float *dE_dh, void *stream) {
   int rc = check_common("egnn_energy", wpack, hidden, layers, n, ht, x, beta, B);
   if (rc) return rc;
-  PITA_REQUIRE(energy, PITA_EINVAL, "egnn_energy: null output");
   if (B == 0) return PITA_OK;
+  PITA_REQUIRE(energy, PITA_EINVAL, "egnn_energy: null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return n == 13 ? launch_energy<13, 13>(wpack, ht, x, beta, B, energy, grad_x, dE_dh, s)
                  : launch_energy<55, 11>(wpack, ht, x, beta, B, energy, grad_x, dE_dh, s);
@@ -964,8 +964,8 @@ extern "C" int pita_egnn_score_div(const float *wpack, int hidden, int layers, i
                                    const float *beta, int64_t B, float *score, float *div, void *stream) {
   int rc = check_common("egnn_score_div", wpack, hidden, layers, n, ht, x, beta, B);
   if (rc) return rc;
-  PITA_REQUIRE(score, PITA_EINVAL, "egnn_score_div: null output");
   if (B == 0) return PITA_OK;
+  PITA_REQUIRE(score, PITA_EINVAL, "egnn_score_div: null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return n == 13 ? launch_score<13, 13, 2>(wpack, ht, x, beta, B, score, div, s)
                  : launch_score<55, 11, 2>(wpack, ht, x, beta, B, score, div, s);

@@ -139,8 +139,9 @@ static int launch_lj(const float *x, int64_t B, float T, float ef, float osc, fl
 extern "C" int pita_lj_energy_force(const float *x, int64_t B, int n, float temperature, float energy_factor,
                                     float oscillator_scale, float *logp, float *force, void *stream) {
   using namespace pita;
-  PITA_REQUIRE(x && logp, PITA_EINVAL, "lj: null pointer");
   PITA_REQUIRE(B >= 0, PITA_EINVAL, "lj: negative batch");
+  if (B == 0) return PITA_OK;  // empty batch: nothing to read or write (pointers may be NULL)
+  PITA_REQUIRE(x && logp, PITA_EINVAL, "lj: null pointer");
   PITA_REQUIRE(aligned16(x) && (force == nullptr || aligned16(force)), PITA_EINVAL, "lj: pointers must be 16-byte aligned");
   PITA_REQUIRE(temperature > 0.f, PITA_EINVAL, "lj: temperature must be positive");
   if (B == 0) return PITA_OK;

@@ -88,6 +88,7 @@ class WeightedSDEIntegrator:
         self.noise_fn: Optional[Callable[[int, torch.Tensor], torch.Tensor]] = None
         self.u0_fn: Optional[Callable[[int], float]] = None
         self._resampler = None
+        self._u0_gen = None
 
     # ------------------------------------------------------------------------------------------
     def maybe_remove_mean(self, x, energy_function):
@@ -100,6 +101,28 @@ class WeightedSDEIntegrator:
         if lm is not None and getattr(lm, "trainer", None) is not None:
             return lm.trainer.world_size, lm.trainer.global_rank
         return world_info(self.process_group)
+
+    def prepare(self, n_local: int, row_floats: int, device):
+        """Sets up the sharded resampler and, with more than one rank, a uniform-offset stream shared by all ranks.
+
+        The reference lets every rank draw u0 from its own CPU generator and relies on `seed_everything` having made
+        them identical (utils.py:112).  With one rank the global CPU generator is used exactly like
+        that; with several, rank 0 draws one seed from it and broadcasts it, so ranks cannot disagree on u0."""
+        self._resampler = ShardedResampler(n_local, row_floats, device, group=self.process_group, exchange=self.exchange)
+        self._u0_gen = None
+        if self._resampler.world > 1:
+            import torch.distributed as dist
+            seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+            seed_dev = seed.to(device)
+            dist.broadcast(seed_dev, src=0, group=self.process_group)
+            self._u0_gen = torch.Generator().manual_seed(int(seed_dev.item()))
+
+    def _draw_u0(self, step: int) -> float:
+        if self.u0_fn is not None:
+            return self.u0_fn(step)
+        if self._u0_gen is not None:
+            return float(torch.rand(size=(1,), dtype=torch.float64, generator=self._u0_gen))
+        return draw_u0()
 
     def _step_scalars(self, t32: float, schedule):
         """Host-side scalar algebra of one step, folded into kernel arguments (float64 on the host)."""
@@ -131,7 +154,7 @@ class WeightedSDEIntegrator:
 
         x = ops.N.as_f32(x1[lo:hi]).clone()
         a = torch.zeros(hi - lo, device=x.device, dtype=torch.float32)
-        self._resampler = ShardedResampler(hi - lo, D, x.device, group=self.process_group, exchange=self.exchange)
+        self.prepare(hi - lo, D, x.device)
         logweights, uniq, sde_terms_all = [], [], []
 
         with torch.no_grad():
@@ -156,7 +179,7 @@ class WeightedSDEIntegrator:
                 a_next = target_logprob + model_energy * sc["gamma"] + a
                 a_full = self._resampler.gather_logweights(a_next)
                 a_full = torch.clamp(a_full, max=torch.quantile(a_full, 0.9))  # one global quantile (:179)
-                u0 = self.u0_fn(S) if self.u0_fn else draw_u0()
+                u0 = self._draw_u0(S)
                 xin = self._stage_for_exchange(x)
                 x, changes = self._resampler.resample(xin, a_full, u0)
                 if self.collect_logweights:
@@ -245,7 +268,7 @@ class WeightedSDEIntegrator:
             return x_next, a_next, B * self._world()[0], terms
         # ---- resample on the global weights (reference :292-295)
         a_full = self._resampler.gather_logweights(a_next)
-        u0 = self.u0_fn(step) if self.u0_fn else draw_u0()
+        u0 = self._draw_u0(step)
         x_res, changes = self._resampler.resample(x_next, a_full, u0)
         return x_res, torch.zeros_like(a_next), changes, terms
 

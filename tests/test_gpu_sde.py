@@ -72,20 +72,15 @@ def _build_integrator(n, sdE, sdS, S, chunk, **kw):
                                  num_negative_time_steps=0, post_mcmc_steps=0, **kw)
 
 
-def test_loop_vs_reference_golden():
-    """integrate_sde end to end on the reference's own trajectory fixture (fp64 reference, fp32 kernels):
-    the same noise / offsets are injected; ancestors must match exactly and x / log-weights to 1e-4."""
-    from pita_b200.annealing_factor_schedules import ConstantAnnealingFactorSchedule
-    from pita_b200.lennardjones_energy import LennardJonesEnergy
-    g = golden("loop_n13.npz")
+def _replay_reference_stream(g, sdE, sdS):
+    """Replays the reference's CPU random stream through the oracle (which reproduces the reference trajectory,
+    tests/test_oracle_golden.py) and returns the per-step noise / offsets it consumed."""
     n, N, S, chunk = int(g["n"]), int(g["N"]), int(g["S"]), int(g["chunk"])
-    sdE, sdS = state_from_golden(g, "E."), state_from_golden(g, "S.")
-    # replay the reference's random stream on the CPU generator (prior, per-chunk noise, u0)
     torch.manual_seed(int(g["seed"]))
     x1 = O.mean_free_prior(N, n, float(g["prior_scale"]), dtype=torch.float64)
     noises, u0s = {}, {}
-    cfg = O.LoopConfig(n=n, steps=S, chunk=chunk, beta=float(g["beta"]), resampling_interval=1, start_resampling_step=1,
-                       end_resampling_step=5, resample_at_end=True)
+    cfg = O.LoopConfig(n=n, steps=S, chunk=chunk, beta=float(g["beta"]), resampling_interval=int(g["interval"]),
+                       start_resampling_step=int(g["start"]), end_resampling_step=int(g["end"]), resample_at_end=True)
 
     def noise_fn(step, xc):
         z = torch.randn_like(xc)
@@ -97,21 +92,57 @@ def test_loop_vs_reference_golden():
         return u0s[step]
 
     x_ref, logw_ref, uniq_ref = O.integrate(sdE, sdS, O.EDMSchedule(0.05), O.ConstGamma(float(g["gamma"])), cfg, x1, noise_fn, u0_fn)
-    assert list(uniq_ref) == list(g["num_unique"])  # the oracle replays the reference
-    integ = _build_integrator(n, sdE, sdS, S, chunk, start_resampling_step=1, end_resampling_step=5, resampling_interval=1,
-                              resample_at_end=True)
-    integ.noise_fn = lambda step, x: torch.cat(noises[step]).float().cuda()
-    integ.u0_fn = lambda step: u0s[step]
+    assert list(uniq_ref) == list(g["num_unique"])
+    return x1, {k: torch.cat(v) for k, v in noises.items()}, u0s
+
+
+def test_loop_vs_reference_golden():
+    """integrate_sde on the reference's own 40-step trajectory fixture (fp64 reference, fp32 kernels), with the
+    reference's noise / offsets injected.  (1) teacher-forced: every step starts from the reference's recorded
+    state and must reproduce the next one to 1e-4 with identical ancestors; (2) free-running: identical
+    ancestor counts at every step and the final particles / end log-weights within a looser bound (errors
+    compound through 40 steps and 18 resamplings)."""
+    from pita_b200.annealing_factor_schedules import ConstantAnnealingFactorSchedule
+    from pita_b200.lennardjones_energy import LennardJonesEnergy
+    g = golden("loop_n13.npz")
+    n, N, S, chunk = int(g["n"]), int(g["N"]), int(g["S"]), int(g["chunk"])
+    sdE, sdS = state_from_golden(g, "E."), state_from_golden(g, "S.")
+    x1, noises, u0s = _replay_reference_stream(g, sdE, sdS)
+    kw = dict(start_resampling_step=int(g["start"]), end_resampling_step=int(g["end"]), resampling_interval=int(g["interval"]),
+              resample_at_end=True)
+    gam = ConstantAnnealingFactorSchedule(float(g["gamma"]))
     tgt = LennardJonesEnergy(dimensionality=3 * n, n_particles=n, temperature=1.0)
-    x, logw, uniq, terms, acc = integ.integrate_sde(x1.float().cuda(), tgt, ConstantAnnealingFactorSchedule(float(g["gamma"])),
-                                                    inverse_temperature=float(g["beta"]))
+    # (1) teacher forced
+    integ = _build_integrator(n, sdE, sdS, S, chunk, **kw)
+    integ.noise_fn = lambda step, x: noises[step].float().cuda()
+    integ.u0_fn = lambda step: u0s[step]
+    integ.prepare(N, 3 * n, "cuda")
+    times = torch.linspace(1.0, 0.0, S + 1)[:-1]
+    dt = 1.0 / S
+    xs = np.concatenate([g["x1"][None].astype(np.float32), g["x_steps"]])
+    a_prev = np.concatenate([np.zeros((1, N)), g["a_steps"]])
+    for step in range(S):
+        x_in = torch.from_numpy(xs[step]).cuda()
+        a_in = torch.from_numpy(a_prev[step]).float().cuda()
+        x_out, a_out, _, _ = integ._fk_step(float(times[step]), step, x_in, a_in, dt, float(np.float32(np.sqrt(dt))),
+                                            float(g["beta"]), n, gam, tgt, int(g["interval"]))
+        assert_close(x_out, xs[step + 1], f"x after step {step} (teacher forced)")
+        assert_close(a_out, g["a_steps"][step], f"a after step {step} (teacher forced)")
+    # (2) free running
+    integ = _build_integrator(n, sdE, sdS, S, chunk, **kw)
+    integ.noise_fn = lambda step, x: noises[step].float().cuda()
+    integ.u0_fn = lambda step: u0s[step]
+    x, logw, uniq, terms, acc = integ.integrate_sde(x1.float().cuda(), tgt, gam, inverse_temperature=float(g["beta"]))
     assert list(uniq) == list(g["num_unique"]), (uniq, list(g["num_unique"]))
-    assert_close(logw, g["logweights"], "logweights vs reference", rtol=2e-4)
-    assert_close(x, g["x_final"], "x_final vs reference", rtol=2e-4)
+    assert logw.shape == g["logweights"].shape
+    assert_close(logw, g["logweights"], "logweights vs reference", rtol=2e-3)
+    assert_close(x, g["x_final"], "x_final vs reference", rtol=2e-3)
 
 
-@pytest.mark.parametrize("n,N,S,chunk", [(13, 96, 4, 32), (55, 12, 3, 6), (13, 50, 3, 16)])
-def test_loop_vs_oracle(n, N, S, chunk):
+@pytest.mark.parametrize("n,N,S,chunk,time_range", [(13, 64, 12, 32, 0.3), (55, 6, 3, 3, 0.06), (13, 50, 8, 16, 0.2)])
+def test_loop_vs_oracle(n, N, S, chunk, time_range):
+    """Free-running loop vs the fp64 oracle with injected noise/offsets, resampling every step, ragged last chunk
+    (N % chunk != 0 in the third case).  Short time ranges keep the explicit Euler map contractive."""
     from pita_b200.annealing_factor_schedules import ConstantAnnealingFactorSchedule
     from pita_b200.lennardjones_energy import LennardJonesEnergy
     sdE = O.random_egnn_state(seed=31 + n, dtype=torch.float64, coord_gain=0.3)
@@ -119,10 +150,11 @@ def test_loop_vs_oracle(n, N, S, chunk):
     gam = 4.0 / 3.0
     sched = O.EDMSchedule(0.05)
     gen = torch.Generator().manual_seed(N)
-    x1 = O.mean_free_prior(N, n, float((sched.h(torch.tensor(1.0)) / gam) ** 0.5), gen=gen, dtype=torch.float64)
+    scale = float((sched.h(torch.tensor(time_range, dtype=torch.float64)) / gam) ** 0.5)
+    x1 = O.centre(O.md_shaped_coords(N, n, seed=N, dtype=torch.float64) + scale * torch.randn(N, 3 * n, generator=gen, dtype=torch.float64), n)
     noise = {s: torch.randn(N, 3 * n, generator=gen, dtype=torch.float64) for s in range(S)}
     u0 = {s: float(torch.rand(1, generator=gen, dtype=torch.float64)) for s in range(S + 1)}
-    cfg = O.LoopConfig(n=n, steps=S, chunk=chunk, beta=0.9, resampling_interval=1)
+    cfg = O.LoopConfig(n=n, steps=S, chunk=chunk, beta=0.9, resampling_interval=1, time_range=time_range)
     cursor = {}
 
     def noise_fn(step, xc):
@@ -131,10 +163,11 @@ def test_loop_vs_oracle(n, N, S, chunk):
         return noise[step][lo:lo + xc.shape[0]]
 
     x_ref, logw_ref, uniq_ref = O.integrate(sdE, sdS, sched, O.ConstGamma(gam), cfg, x1, noise_fn, lambda s: u0[s])
-    integ = _build_integrator(n, sdE, sdS, S, chunk, start_resampling_step=0, end_resampling_step=10 ** 9, resampling_interval=1)
+    integ = _build_integrator(n, sdE, sdS, S, chunk, start_resampling_step=0, end_resampling_step=10 ** 9, resampling_interval=1,
+                              time_range=time_range)
     integ.noise_fn = lambda step, x: noise[step].float().cuda()
     integ.u0_fn = lambda step: u0[step]
     tgt = LennardJonesEnergy(dimensionality=3 * n, n_particles=n)
     x, logw, uniq, _, _ = integ.integrate_sde(x1.float().cuda(), tgt, ConstantAnnealingFactorSchedule(gam), inverse_temperature=0.9)
     assert list(uniq) == list(uniq_ref)
-    assert_close(x, x_ref, "x_final", rtol=2e-4)
+    assert_close(x, x_ref, "x_final", rtol=1e-3)

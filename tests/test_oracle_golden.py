@@ -113,8 +113,8 @@ def test_loop_matches_reference(golden_dir):
     torch.manual_seed(int(g["seed"]))
     x1 = O.mean_free_prior(N, n, float(g["prior_scale"]), dtype=torch.float64)
     _close(x1, g["x1"], 1e-13, "prior")
-    cfg = O.LoopConfig(n=n, steps=S, chunk=chunk, beta=float(g["beta"]), resampling_interval=1,
-                       start_resampling_step=1, end_resampling_step=5, resample_at_end=True)
+    cfg = O.LoopConfig(n=n, steps=S, chunk=chunk, beta=float(g["beta"]), resampling_interval=int(g["interval"]),
+                       start_resampling_step=int(g["start"]), end_resampling_step=int(g["end"]), resample_at_end=True)
     x, logw, uniq = O.integrate(
         sdE, sdS, sched, gam, cfg, x1,
         noise_fn=lambda step, xc: torch.randn_like(xc),
