@@ -154,6 +154,13 @@ int pita_mala_accept(float *x, float *logp, const float *x_prop, const float *lo
                      const float *log_q_fwd, const float *uniform, int64_t B, int n, float dt, int remove_mean,
                      float *accepted, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Self-test of the sm_100a tensor-core plumbing (tcgen05.mma kind::tf32, TMEM, mbarrier) used by the EGNN
+ * tangent kernel: D[128][32] = A[128][32] * B[32][32]^T on one CTA.  split=1: 3xTF32 (fp32-accurate).
+ * No reference counterpart; exists so the tests can pin descriptor / swizzle conventions on hardware.
+ * ------------------------------------------------------------------------------------------------ */
+int pita_umma_selftest(const float *A, const float *B, float *D, int split, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
