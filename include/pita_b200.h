@@ -66,9 +66,19 @@ int pita_egnn_energy(const float *wpack, int hidden, int layers, int n, const fl
 
 /* ScoreNet.forward (models/components/score_net.py:13-43) and the exact divergence
  * tr(d score / d x) of compute_divergence_exact (models/components/utils.py:43-51):
- * score[B][3n], div[B] (NULL to skip the divergence). */
+ * score[B][3n], div[B] (NULL to skip the divergence).
+ * mode selects how the dense tangent contraction of the divergence is evaluated:
+ *   PITA_DIV_FP32   fp32 CUDA cores (reference-accurate, slowest)
+ *   PITA_DIV_3XTF32 tcgen05 tensor cores, error-compensated 3xTF32 (fp32-accurate; the default)
+ *   PITA_DIV_TF32   tcgen05 tensor cores, plain TF32 (looser: ~1e-3 on the network part of the divergence)
+ * The tensor-core modes need `workspace` (device, >= pita_egnn_score_div_workspace_bytes(n, mode) bytes). */
+#define PITA_DIV_FP32 0
+#define PITA_DIV_3XTF32 1
+#define PITA_DIV_TF32 2
+int64_t pita_egnn_score_div_workspace_bytes(int n, int mode);
 int pita_egnn_score_div(const float *wpack, int hidden, int layers, int n, const float *ht, const float *x,
-                        const float *beta, int64_t B, float *score, float *div, void *stream);
+                        const float *beta, int64_t B, float *score, float *div, int mode, void *workspace,
+                        int64_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused Euler-Maruyama + Feynman-Kac step.  Replaces, for one step over the rank-local particles:

@@ -30,7 +30,7 @@ def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = _sources() + [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "umma.cuh"),
+    deps = _sources() + [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "umma.cuh"), os.path.join(_CSRC, "egnn_common.cuh"),
                          os.path.join(_HERE, "..", "include", "pita_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(
                 os.path.getmtime(src), os.path.getmtime(os.path.join(_CSRC, "common.cuh")),
-                os.path.getmtime(os.path.join(_CSRC, "umma.cuh")),
+                os.path.getmtime(os.path.join(_CSRC, "umma.cuh")), os.path.getmtime(os.path.join(_CSRC, "egnn_common.cuh")),
                 os.path.getmtime(os.path.join(_HERE, "..", "include", "pita_b200.h"))):
             continue
         cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
@@ -91,7 +91,8 @@ SIGNATURES = {
     "pita_egnn_pack_floats": (_I64, [_I, _I]),
     "pita_egnn_forward": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P]),
     "pita_egnn_energy": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P, _P, _P]),
-    "pita_egnn_score_div": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P, _P]),
+    "pita_egnn_score_div_workspace_bytes": (_I64, [_I, _I]),
+    "pita_egnn_score_div": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P, _I, _P, _I64, _P]),
     "pita_sde_fk_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _I64, _I, ctypes.POINTER(_SdeParams), _P, _P, _P]),
     "pita_fk_quantile_accumulate": (_I, [_P, _P, _I64, _I, _F, _F, _I, _P, _P, _P]),
     "pita_resample_workspace_bytes": (_I64, [_I64]),

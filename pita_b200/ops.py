@@ -67,15 +67,35 @@ def egnn_energy(wpack, hidden, layers, n, ht, x, beta, need_grad=True, need_dh=T
     return e, g, dh
 
 
-def egnn_score_div(wpack, hidden, layers, n, ht, x, beta, need_div=True):
+DIV_MODES = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+_div_ws = {}
+
+
+def default_div_mode() -> str:
+    """PITA_DIV_MODE=fp32|3xtf32|tf32 (default 3xtf32: tensor cores, fp32-accurate)."""
+    import os
+    return os.environ.get("PITA_DIV_MODE", "3xtf32").lower()
+
+
+def egnn_score_div(wpack, hidden, layers, n, ht, x, beta, need_div=True, mode=None):
     lib = N.load()
     x = N.as_f32(x)
     B = x.shape[0]
     ht, beta = _expand(ht, B, x.device), _expand(beta, B, x.device)
     s = torch.empty_like(x)
     d = torch.empty(B, device=x.device, dtype=torch.float32) if need_div else None
-    N.check(lib.pita_egnn_score_div(N.ptr(wpack), hidden, layers, n, N.ptr(ht), N.ptr(x), N.ptr(beta), B, N.ptr(s), N.ptr(d),
-                                    N.stream_ptr(x.device)), "pita_egnn_score_div")
+    m = DIV_MODES[(mode or default_div_mode())]
+    ws, ws_bytes = None, 0
+    if need_div and m != 0:
+        ws_bytes = int(lib.pita_egnn_score_div_workspace_bytes(n, m))
+        key = (str(x.device), torch.cuda.current_stream(x.device).cuda_stream)
+        ws = _div_ws.get(key)
+        if ws is None or ws.numel() < ws_bytes:
+            ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+            _div_ws[key] = ws
+    N.check(lib.pita_egnn_score_div(N.ptr(wpack), hidden, layers, n, N.ptr(ht), N.ptr(x), N.ptr(beta), B, N.ptr(s), N.ptr(d), m,
+                                    None if ws is None else ws.data_ptr(), ws_bytes, N.stream_ptr(x.device)),
+            "pita_egnn_score_div")
     return s, d
 
 

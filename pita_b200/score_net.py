@@ -12,15 +12,16 @@ from . import ops
 
 
 class ScoreNet(nn.Module):
-    def __init__(self, model: nn.Module, precondition_beta: Optional[bool] = False):
+    def __init__(self, model: nn.Module, precondition_beta: Optional[bool] = False, div_mode: Optional[str] = None):
         super().__init__()
         self.model = model
         self.precondition_beta = precondition_beta
+        self.div_mode = div_mode  # None -> PITA_DIV_MODE / "3xtf32"; "fp32" | "3xtf32" | "tf32"
 
     def score_and_divergence(self, h_t, x_t, beta, need_div=True):
         m = self.model
         s, d = ops.egnn_score_div(m.packed_weights(x_t.device), m.hidden_nf, m.n_layers, m._n_particles, h_t, x_t, beta,
-                                  need_div=need_div)
+                                  need_div=need_div, mode=self.div_mode)
         if self.precondition_beta:  # :37-38; the divergence is linear in the score
             b = ops._expand(beta, x_t.shape[0], x_t.device)
             s = s * b[:, None]
