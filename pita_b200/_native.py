@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpita_b200.so")
-SOURCES = ["capi.cu", "lj.cu", "resample.cu", "sde.cu", "egnn.cu", "egnn_mma.cu", "umma_selftest.cu"]
+SOURCES = ["capi.cu", "lj.cu", "resample.cu", "sde.cu", "egnn.cu", "egnn_mma.cu", "egnn_rows.cu", "umma_selftest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -30,7 +30,7 @@ def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = _sources() + [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "umma.cuh"), os.path.join(_CSRC, "egnn_common.cuh"),
+    deps = _sources() + [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "umma.cuh"), os.path.join(_CSRC, "egnn_common.cuh"), os.path.join(_CSRC, "rowgemm.cuh"),
                          os.path.join(_HERE, "..", "include", "pita_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -50,6 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(
                 os.path.getmtime(src), os.path.getmtime(os.path.join(_CSRC, "common.cuh")),
                 os.path.getmtime(os.path.join(_CSRC, "umma.cuh")), os.path.getmtime(os.path.join(_CSRC, "egnn_common.cuh")),
+                os.path.getmtime(os.path.join(_CSRC, "rowgemm.cuh")),
                 os.path.getmtime(os.path.join(_HERE, "..", "include", "pita_b200.h"))):
             continue
         cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]

@@ -51,8 +51,34 @@ __device__ __forceinline__ float fast_rcp(float v) {
   return r;
 }
 
-// logistic sigmoid; |rel err| ~ 3e-7 (ex2.approx + rcp.approx)
-__device__ __forceinline__ float sigmoidf_fast(float z) { return fast_rcp(1.0f + __expf(-z)); }
+__device__ __forceinline__ float fast_ex2(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// logistic sigmoid; |rel err| ~ 3e-7 (ex2.approx + rcp.approx; flush-to-zero forms: no range fix-up code)
+__device__ __forceinline__ float sigmoidf_fast(float z) { return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * z)); }
+
+// explicit shared-space 128-bit accesses (generic pointers into dynamic shared memory otherwise compile to LD.E/ST.E)
+__device__ __forceinline__ float4 lds4(const float *p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p)))
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts4(float *p, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float lds1(const float *p) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))) : "memory");
+  return v;
+}
 
 // SiLU value and derivative from one sigmoid:  silu = z*s,  silu' = s*(1 + z*(1-s))
 __device__ __forceinline__ void silu_both(float z, float &val, float &der) {

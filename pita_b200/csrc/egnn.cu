@@ -667,6 +667,17 @@ static int check_common(const char *what, const float *w, int hidden, int layers
 
 }  // namespace pita
 
+namespace pita {
+int launch_forward_rows(int n, bool split, const float *w, const float *tc, const float *y, const float *beta, int64_t B,
+                        float *vel, cudaStream_t s);
+int64_t score_div_rows_workspace_bytes(int n);
+int launch_score_div_rows(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,
+                          float *sc, float *dv, float *scratch, int64_t scratch_bytes, cudaStream_t s);
+int64_t score_div_mma_workspace_bytes(int n);
+int launch_score_div_mma(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,
+                         float *sc, float *dv, float *scratch, int64_t scratch_bytes, cudaStream_t s);
+}  // namespace pita
+
 using namespace pita;
 
 extern "C" int64_t pita_egnn_pack_floats(int hidden, int layers) {
@@ -681,7 +692,7 @@ extern "C" int pita_egnn_forward(const float *wpack, int hidden, int layers, int
   if (B == 0) return PITA_OK;
   PITA_REQUIRE(vel, PITA_EINVAL, "egnn_forward: null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return n == 13 ? launch_forward<13, 13>(wpack, tcond, y, beta, B, vel, s) : launch_forward<55, 11>(wpack, tcond, y, beta, B, vel, s);
+  return launch_forward_rows(n, true, wpack, tcond, y, beta, B, vel, s);
 }
 
 extern "C" int pita_egnn_energy(const float *wpack, int hidden, int layers, int n, const float *ht, const float *x,
@@ -695,15 +706,10 @@ extern "C" int pita_egnn_energy(const float *wpack, int hidden, int layers, int 
                  : launch_energy<55, 11>(wpack, ht, x, beta, B, energy, grad_x, dE_dh, s);
 }
 
-namespace pita {
-int64_t score_div_mma_workspace_bytes(int n);
-int launch_score_div_mma(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,
-                         float *sc, float *dv, float *scratch, int64_t scratch_bytes, cudaStream_t s);
-}  // namespace pita
 
 extern "C" int64_t pita_egnn_score_div_workspace_bytes(int n, int mode) {
   if (mode == PITA_DIV_FP32) return 0;
-  return pita::score_div_mma_workspace_bytes(n);
+  return pita::score_div_rows_workspace_bytes(n);
 }
 
 extern "C" int pita_egnn_score_div(const float *wpack, int hidden, int layers, int n, const float *ht, const float *x,
@@ -715,9 +721,9 @@ extern "C" int pita_egnn_score_div(const float *wpack, int hidden, int layers, i
   PITA_REQUIRE(score, PITA_EINVAL, "egnn_score_div: null output");
   PITA_REQUIRE(mode >= 0 && mode <= 2, PITA_EINVAL, "egnn_score_div: mode must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (mode == PITA_DIV_FP32 || div == nullptr)
+  if (mode == PITA_DIV_FP32)
     return n == 13 ? launch_score<13, 13, 2>(wpack, ht, x, beta, B, score, div, s)
                    : launch_score<55, 11, 2>(wpack, ht, x, beta, B, score, div, s);
-  return launch_score_div_mma(n, mode == PITA_DIV_3XTF32, wpack, ht, x, beta, B, score, div, static_cast<float *>(workspace),
-                              workspace_bytes, s);
+  return launch_score_div_rows(n, mode == PITA_DIV_3XTF32, wpack, ht, x, beta, B, score, div, static_cast<float *>(workspace),
+                               workspace_bytes, s);
 }

@@ -1,0 +1,1004 @@
+// EGNN denoiser on the row-batched tcgen05 engine (rowgemm.cuh): plain forward (EGNN_dynamics.forward,
+// egnn_temp_conditioned.py:56-93) and score + exact divergence (score_net.py:13-43, utils.py:30-51).
+// See rowgemm.cuh for the thread = (particle, node) row mapping; the derivative algebra follows
+// oracle/egnn_analytic.py (checked there against autograd on the CPU).
+#include "rowgemm.cuh"
+
+namespace pita {
+namespace rg {
+
+// TMEM column slots (32 columns each) of one team
+enum Slot { sAcc0 = 0, sAccC = 1, sT0 = 2, sT1 = 3, sT2 = 4, sP = 5, sPA = 6, sH = 7, kSlots = 8 };
+// weight slots
+enum WSlot { wA = 0, wB = 1, wW2 = 2, wWc1 = 3, wW3a = 4 };
+
+template <int NP>
+struct Shape {
+  static constexpr int PB = kRows / NP;  // particles per team tile
+  static constexpr int R = PB * NP;      // active rows
+};
+
+// ---- shared-memory plan -------------------------------------------------------------------------
+template <int NP, int NTEAM, bool SPLIT, bool TANGENT>
+struct Smem {
+  static constexpr int PB = Shape<NP>::PB;
+  // byte offsets from a 1024-aligned base
+  static constexpr size_t oW = 0;
+  static constexpr size_t oA = oW + (size_t)kWSlots * Bytes<SPLIT>::kW;
+  static constexpr size_t oF = oA + (size_t)NTEAM * Bytes<SPLIT>::kA;  // float regions start here
+  // CTA-wide float regions (float index relative to oF)
+  static constexpr int fVec = 0;                            // [3][kNumVec][32]
+  static constexpr int fEmb = fVec + 3 * kNumVec * 32;      // [3][32] embedding e0 e1 eb
+  static constexpr int fCls = fEmb + 96;                    // layer-0 class tables: P0c[3][32], Q0c[3][32]
+  static constexpr int fMisc = fCls + 192;                  // mbarriers [NTEAM] (8 B each) + tmem slot
+  static constexpr int fTeam = fMisc + 2 * NTEAM + 8;
+  // per-team float regions
+  static constexpr int tQa = 0;                             // [128][32] swizzled: Q rows of layer 1 (persist in tangent passes)
+  static constexpr int tQb = tQa + kRows * 32;              // [128][32] swizzled: Q rows of layers 0 / 2; sender tangent base vectors
+  static constexpr int tX = tQb + kRows * 32;               // [3 or 4][128] float4 (x^3 aliases tDX in the tangent kernel)
+  static constexpr int tDX = tX + (TANGENT ? 3 : 4) * kRows * 4;  // [128][3] float4   sender-side coordinate tangents
+  static constexpr int tX3 = TANGENT ? tDX : tX + 3 * kRows * 4;
+  static constexpr int tCoef = tDX + (TANGENT ? kRows * 12 : 0);  // [128] float4  sender-side coefficients
+  static constexpr int tOwnA = tCoef + (TANGENT ? kRows * 4 : 0); // [PB][3][32]   A1 dh1 of the tangent node (own dirs)
+  static constexpr int tKdP2 = tOwnA;                             // [PB][3][32]   A2 dh2 of the tangent node (layer-2 stage only)
+  static constexpr int tOwnB = tOwnA + (TANGENT ? PB * 96 : 0);   // [PB][3][32]   B1 dh1 of the tangent node
+  static constexpr int tKP2 = tOwnB + (TANGENT ? PB * 96 : 0);    // [PB][32]      P2 of the tangent node
+  static constexpr int tRed = tKP2 + (TANGENT ? PB * 32 : 0);     // [128]         per-particle reductions
+  static constexpr int kTeamFloats = ((tRed + kRows + 3) / 4) * 4;
+  static constexpr size_t kBytes = 1024 + oF + (size_t)(fTeam + NTEAM * kTeamFloats) * 4;
+};
+
+// ---- element-wise stages of one edge ----------------------------------------------------------------
+// stage 1: z1 = P_i + Q_j + c1 r2 + d1 ea  ->  row = silu(z1), f1 = silu'(z1)
+template <bool KEEP, bool HAS_Q = true>
+__device__ __forceinline__ void stage1(float (&row)[32], float (&f1)[32], const float *qbase, int qrow, const float *vec, float r2,
+                                       float ea) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 q = HAS_Q ? qrow_ld4(qbase, qrow, k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 c = lds4(vec + vC1 * 32 + 4 * k4);
+    const float4 d = lds4(vec + vD1 * 32 + 4 * k4);
+    const float qq[4] = {q.x, q.y, q.z, q.w}, cc[4] = {c.x, c.y, c.z, c.w}, dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 4 * k4 + e;
+      const float z = row[k] + qq[e] + cc[e] * r2 + dd[e] * ea;
+      float a, f;
+      silu_both(z, a, f);
+      row[k] = a;
+      if (KEEP) f1[k] = f;
+    }
+  }
+}
+
+// stage 2: z2 = acc + b2 -> m = silu(z2), f2; attention gate; row = m * att.  Returns att.
+template <bool KEEP>
+__device__ __forceinline__ float stage2(float (&row)[32], float (&m)[32], float (&f2)[32], const float *vec) {
+  float dot = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 b = lds4(vec + vB2 * 32 + 4 * k4);
+    const float4 w = lds4(vec + vWA * 32 + 4 * k4);
+    const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 4 * k4 + e;
+      float a, f;
+      silu_both(row[k] + bb[e], a, f);
+      row[k] = a;
+      if (KEEP) { m[k] = a; f2[k] = f; }
+      dot = fmaf(ww[e], a, dot);
+    }
+  }
+  const float att = sigmoidf_fast(dot + lds1(vec + vBA * 32));
+#pragma unroll
+  for (int k = 0; k < 32; ++k) row[k] *= att;
+  return att;
+}
+
+// stage 3: zc = acc + bc1 -> u = <wc2, silu(zc)>, th = tanh(u); fc = silu'(zc)
+template <bool KEEP>
+__device__ __forceinline__ float stage3(const float (&acc)[32], float (&fc)[32], const float *vec) {
+  float u = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 b = lds4(vec + vBC1 * 32 + 4 * k4);
+    const float4 w = lds4(vec + vWC2 * 32 + 4 * k4);
+    const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 4 * k4 + e;
+      float a, f;
+      silu_both(acc[k] + bb[e], a, f);
+      if (KEEP) fc[k] = f;
+      u = fmaf(ww[e], a, u);
+    }
+  }
+  return tanhf(u);
+}
+
+__device__ __forceinline__ void add_vec(float (&row)[32], const float *vec32) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 b = lds4(vec32 + 4 * k4);
+    row[4 * k4] += b.x; row[4 * k4 + 1] += b.y; row[4 * k4 + 2] += b.z; row[4 * k4 + 3] += b.w;
+  }
+}
+
+// ---- common context --------------------------------------------------------------------------------
+template <int NP, int NTEAM, bool SPLIT, bool TANGENT>
+struct Ctx {
+  using S = Smem<NP, NTEAM, SPLIT, TANGENT>;
+  static constexpr int PB = Shape<NP>::PB;
+  static constexpr int R = Shape<NP>::R;
+  Team<SPLIT> T;
+  float *wsm, *sVec, *sEmb, *sCls, *tm;  // CTA regions and this team's float region
+  float4 *sX, *sX3;
+  float *sQa, *sQb;
+  int tid, team, p, i;
+  bool row_ok;  // tt < R
+
+  __device__ __forceinline__ const float *vec(int l) const { return sVec + l * kNumVec * 32; }
+  __device__ __forceinline__ int sender(int u) const { int j = i + 1 + u; return j >= NP ? j - NP : j; }
+};
+
+// One-time CTA setup: carve shared memory, TMEM, mbarriers, per-layer vectors.
+template <int NP, int NTEAM, bool SPLIT, bool TANGENT>
+__device__ __forceinline__ void setup(Ctx<NP, NTEAM, SPLIT, TANGENT> &c, float *sm_raw, const float *__restrict__ wpack,
+                                      uint32_t &tmem_base_out) {
+  using S = Smem<NP, NTEAM, SPLIT, TANGENT>;
+  uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+  c.tid = threadIdx.x;
+  c.team = c.tid >> 7;
+  const int tt = c.tid & 127, warp = c.tid >> 5;
+  c.wsm = reinterpret_cast<float *>(base + S::oW);
+  float *fl = reinterpret_cast<float *>(base + S::oF);
+  c.sVec = fl + S::fVec;
+  c.sEmb = fl + S::fEmb;
+  c.sCls = fl + S::fCls;
+  uint64_t *mbars = reinterpret_cast<uint64_t *>(fl + S::fMisc);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fl + S::fMisc + 2 * NTEAM);
+  c.tm = fl + S::fTeam + c.team * S::kTeamFloats;
+  c.sQa = c.tm + S::tQa;
+  c.sQb = c.tm + S::tQb;
+  c.sX = reinterpret_cast<float4 *>(c.tm + S::tX);
+  c.sX3 = reinterpret_cast<float4 *>(c.tm + S::tX3);
+  c.p = tt / NP;
+  c.i = tt - c.p * NP;
+  c.row_ok = tt < Shape<NP>::R;
+
+  if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+  if (c.tid == 0) {
+    for (int k = 0; k < NTEAM; ++k) umma::mbar_init(mbars + k, 1);
+    umma::fence_mbar_init();
+  }
+  for (int k = c.tid; k < 3 * kNumVec * 32; k += NTEAM * 128) {
+    const int l = k / (kNumVec * 32), r = k % (kNumVec * 32);
+    c.sVec[k] = __ldg(wpack + pk::kHeader + l * pk::kLayer + pk::c1 + r);
+  }
+  for (int k = c.tid; k < 96; k += NTEAM * 128) c.sEmb[k] = __ldg(wpack + k);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem_base = uniform32(*tmem_slot);
+  tmem_base_out = tmem_base;
+  const uint32_t team_u = uniform32((uint32_t)c.team);
+  c.T.a_hi = reinterpret_cast<float *>(base + S::oA + (size_t)c.team * Bytes<SPLIT>::kA);
+  c.T.a_addr = uniform32(umma::smem_u32(base + S::oA)) + team_u * (uint32_t)Bytes<SPLIT>::kA;
+  c.T.w_addr = uniform32(umma::smem_u32(c.wsm));
+  c.T.mbar_addr = uniform32(umma::smem_u32(mbars)) + team_u * 8u;
+  c.T.phase = 0;
+  c.T.tmem_col = tmem_base + team_u * (uint32_t)(512 / NTEAM);
+  c.T.tmem = c.T.tmem_col + (((uint32_t)((warp & 3) * 32)) << 16);
+  c.T.bar_id = 1 + c.team;
+  c.T.tt = tt;
+  c.T.issuer = uniform32((uint32_t)(warp & 3)) == 0u;
+}
+
+template <int NP, int NTEAM, bool SPLIT, bool TANGENT>
+__device__ __forceinline__ void load_weights(Ctx<NP, NTEAM, SPLIT, TANGENT> &c, const WeightSrc &src) {
+  __syncthreads();  // every team is done with the MMAs that read the old tiles
+  load_weight_tiles<SPLIT>(c.wsm, src, c.tid, NTEAM * 128);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+}
+
+__device__ __forceinline__ WeightSrc layer_edge_set(const float *Wl) {
+  WeightSrc s;
+  s.p[wA] = Wl + pk::A_b; s.p[wB] = Wl + pk::B_b; s.p[wW2] = Wl + pk::W2_b; s.p[wWc1] = Wl + pk::Wc1_b; s.p[wW3a] = Wl + pk::W3a_b;
+  s.count = 5;
+  return s;
+}
+
+// Node embedding h^0 of the thread's node (egnn_temp_conditioned.py:63-78: node k sees (f[2k], f[2k+1]) of
+// f = [t]*n ++ [beta]*n).
+template <int NP>
+__device__ __forceinline__ void embed(float (&h)[32], const float *sEmb, int i, float tcond, float beta) {
+  const float f0 = (2 * i < NP) ? tcond : beta;
+  const float f1 = (2 * i + 1 < NP) ? tcond : beta;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) h[k] = fmaf(sEmb[k], f0, fmaf(sEmb[32 + k], f1, sEmb[64 + k]));
+}
+
+// Primal forward of the three layers for the team's PB particles.
+//   in : sX[0] = network input coordinates (published, team-synced by the caller), tcond/beta of the thread's particle
+//   out: sX[1..3]; TMEM sP = P^1 (+b1) if KEEP_L1; sQa = Q^1.  When `scratch` != nullptr the per-row vectors the
+//        tangent passes need later are written there: f3^0, f3^1 (silu'(z3)), P^2 (+b1), Q^2   (own-row layout).
+template <int NP, int NTEAM, bool SPLIT, bool TANGENT>
+__device__ __forceinline__ void primal_forward_rows(Ctx<NP, NTEAM, SPLIT, TANGENT> &c, const float *__restrict__ wpack,
+                                                    float tcond, float beta, bool team_active, float *scratch_row) {
+  constexpr int L = 3;
+  const float rng = kCoordsRange / (float)L;
+  Team<SPLIT> &T = c.T;
+  const int tt = T.tt;
+  float row[32];
+  float dummy[32];
+  if (team_active) {
+    embed<NP>(row, c.sEmb, c.i, tcond, beta);
+    T.st(sH, row);
+  }
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    const float *Wl = wpack + pk::kHeader + l * pk::kLayer;
+    const float *vec = c.vec(l);
+    load_weights(c, layer_edge_set(Wl));
+    float *sQ = (l == 1) ? c.sQa : c.sQb;
+    if (team_active) {
+      // ---- node products P = A h + b1, Q = B h
+      T.ld(sH, row);
+      T.store_row(row);
+      T.round_trip([&] { T.mma(sP, wA, false); T.mma(sAcc0, wB, false); });
+      T.ld(sAcc0, row);
+      qrow_store(sQ, tt, row);
+      T.ld(sP, row);
+      add_vec(row, vec + vB1 * 32);
+      T.st(sP, row);
+      if (TANGENT && scratch_row) {
+        if (l == 1) store_vec_global(scratch_row + 4 * kRows * 32, row);  // P^1
+        if (l == 2) {
+          store_vec_global(scratch_row + 2 * kRows * 32, row);  // P^2
+          float q[32];
+          qrow_load(sQ, tt, q);
+          store_vec_global(scratch_row + 3 * kRows * 32, q);    // Q^2
+        }
+      }
+      umma::fence_before_thread_sync();
+      T.sync();  // Q rows and TMEM stores visible before the gathers / next MMAs
+      umma::fence_after_thread_sync();
+      // ---- edges
+      const float4 xi = c.sX[l * kRows + tt], x0i = c.sX[tt];
+      float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+#pragma unroll 1
+      for (int u = 0; u < NP - 1; ++u) {
+        const int rj = c.p * NP + c.sender(u);
+        const Geo g = edge_geo4(xi, c.sX[l * kRows + rj], x0i, c.sX[rj]);
+        T.ld(sP, row);
+        stage1<false>(row, dummy, sQ, rj, vec, g.r2, g.ea);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAcc0, wW2, false); });
+        T.ld(sAcc0, row);
+        stage2<false>(row, dummy, dummy, vec);
+        T.store_row(row);
+        const bool accz = u > 0;
+        T.round_trip([&] { T.mma(sAccC, wWc1, false); if (l < L - 1) T.mma(sT0, wW3a, accz); });
+        T.ld(sAccC, row);
+        const float th = stage3<false>(row, dummy, vec);
+        const float f = g.inv * th * rng;
+        dx0 = fmaf(g.d0, f, dx0); dx1 = fmaf(g.d1, f, dx1); dx2 = fmaf(g.d2, f, dx2);
+      }
+      (l == L - 1 ? c.sX3 : c.sX + (l + 1) * kRows)[tt] = make_float4(xi.x + dx0, xi.y + dx1, xi.z + dx2, 0.f);
+    }
+    if (l < L - 1) {
+      // ---- node update h += W4 silu(W3h h + W3a agg + b3) + b4
+      WeightSrc s2;
+      s2.p[0] = Wl + pk::W3h_b;
+      s2.p[1] = Wl + pk::W4_b;
+      s2.count = 2;
+      load_weights(c, s2);
+      if (team_active) {
+        T.ld(sH, row);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sT0, 0, true); });
+        T.ld(sT0, row);
+        add_vec(row, vec + vB3 * 32);
+        if (TANGENT && scratch_row) {
+          float f3[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) { float a; silu_both(row[k], a, f3[k]); row[k] = a; }
+          store_vec_global(scratch_row + l * kRows * 32, f3);  // f3^l
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) row[k] = silu_val(row[k]);
+        }
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAcc0, 1, false); });
+        float hh[32];
+        T.ld(sH, hh);
+        T.ld(sAcc0, row);
+        add_vec(row, vec + vB4 * 32);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) hh[k] += row[k];
+        T.st(sH, hh);
+      }
+    }
+  }
+  if (team_active) {
+    umma::fence_before_thread_sync();
+    T.sync();
+    umma::fence_after_thread_sync();
+  }
+}
+
+// Per-particle mean over the NP rows of a particle of a float4 held by each row (team-wide helper).
+// `buf` is a [128] float4 scratch in shared memory; all threads of the team call.
+template <int NP, bool SPLIT>
+__device__ __forceinline__ float4 particle_mean(const Team<SPLIT> &T, float4 *buf, float4 v, int p) {
+  T.sync();
+  buf[T.tt] = v;
+  T.sync();
+  float a = 0.f, b = 0.f, cc = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < NP; ++k) {
+    const float4 q = buf[p * NP + k];
+    a += q.x; b += q.y; cc += q.z;
+  }
+  return make_float4(a / NP, b / NP, cc / NP, 0.f);
+}
+
+// ================================================================================================
+// Kernel: plain forward   vel = EGNN_dynamics(tcond, y, beta)
+// ================================================================================================
+template <int NP, int NTEAM, bool SPLIT>
+__global__ void __launch_bounds__(NTEAM * 128, 1)
+egnn_forward_rows_kernel(const float *__restrict__ wpack, const float *__restrict__ tcond, const float *__restrict__ y,
+                         const float *__restrict__ beta, int64_t B, float *__restrict__ vel) {
+  extern __shared__ __align__(16) float sm_raw[];
+  using C = Ctx<NP, NTEAM, SPLIT, false>;
+  C c;
+  uint32_t tmem_base;
+  setup(c, sm_raw, wpack, tmem_base);
+  constexpr int PB = C::PB;
+  const int64_t nbatch = (B + (int64_t)NTEAM * PB - 1) / ((int64_t)NTEAM * PB);
+  for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    const int64_t p0 = (batch * NTEAM + c.team) * PB;
+    const bool team_active = p0 < B;
+    const int64_t part = p0 + c.p;
+    const bool ok = c.row_ok && part < B;
+    const int64_t pc = ok ? part : (B - 1);
+    const int ic = c.row_ok ? c.i : 0;
+    const float tc = __ldg(tcond + pc), be = __ldg(beta + pc);
+    const float *src = y + pc * 3 * NP + 3 * ic;
+    const float4 y0 = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), 0.f);
+    c.sX[c.T.tt] = y0;
+    primal_forward_rows(c, wpack, tc, be, team_active, nullptr);
+    if (team_active) {
+      const float4 xl = c.sX3[c.T.tt];
+      const float4 v = make_float4(xl.x - y0.x, xl.y - y0.y, xl.z - y0.z, 0.f);
+      const float4 mean = particle_mean<NP, SPLIT>(c.T, reinterpret_cast<float4 *>(c.sQb), v, c.row_ok ? c.p : 0);
+      if (ok) {
+        float *dst = vel + part * 3 * NP + 3 * c.i;
+        dst[0] = v.x - mean.x; dst[1] = v.y - mean.y; dst[2] = v.z - mean.z;
+      }
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if ((c.tid >> 5) == 0) umma::tmem_dealloc<512>(tmem_base);
+}
+
+template <int NP, int NTEAM, bool SPLIT>
+static int launch_forward_rows(const float *w, const float *tc, const float *y, const float *beta, int64_t B, float *vel,
+                               cudaStream_t s) {
+  using S = Smem<NP, NTEAM, SPLIT, false>;
+  auto k = egnn_forward_rows_kernel<NP, NTEAM, SPLIT>;
+  static_assert(S::kBytes <= 227 * 1024, "shared memory plan exceeds 227 KB");
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes);
+  if (e != cudaSuccess) { set_error("egnn_forward_rows_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PITA_ECUDA; }
+  const int64_t nbatch = (B + (int64_t)NTEAM * Shape<NP>::PB - 1) / ((int64_t)NTEAM * Shape<NP>::PB);
+  const unsigned grid = (unsigned)(nbatch < kNumSMs ? nbatch : kNumSMs);
+  k<<<grid, NTEAM * 128, S::kBytes, s>>>(w, tc, y, beta, B, vel);
+  PITA_CHECK_LAUNCH("egnn_forward_rows_kernel");
+  return PITA_OK;
+}
+
+
+// ================================================================================================
+// Kernel: score + exact divergence (forward-mode tangents on the row engine)
+//
+// trace = sum_k sum_a d x^3[k,a] / d y[k,a] is accumulated in NP passes, pass k carrying the three directions
+// (k, a) of every particle of the tile at once.  Structure used (oracle/egnn_analytic.py):
+//   layer 0: h^0 does not depend on y, so for i != k the tangent of node i is rank one,
+//            dh^1_i[(k,a)] = cf_a * omega_ik,  cf_a = -2 (y_i - y_k)_a,  omega_ik = W4 (f3_i * W3a wvec_ik),
+//            wvec_ik = d ms_ik / d r2 (one extra row through W2); for i == k it is the sum over i's 12 edges,
+//            pre-computed for every node in a pre-phase (own-direction vectors, kept in the scratch buffer);
+//   layer 1: dense — every receiver row walks its n-1 sender slots, 3 tangent rows per edge through W2 and
+//            Wc1, the aggregate through W3a accumulated over slots inside TMEM;
+//   layer 2: only d x^3_k / d y_k is needed: edge (k, j) is evaluated by the SENDER's thread j.
+// ================================================================================================
+enum Scr { qF30 = 0, qF31 = 1, qP2 = 2, qQ2 = 3, qP1 = 4, qOmega = 5, qDh1o = 6, qPiAo = 9, qPiBo = 12, qDxo = 15, kScrVecs = 16 };
+
+// acc = W2 dz1  ->  d(ms) in place:  dm = f2*acc, ds = att(1-att) <wa, dm>, dms = dm*att + m*ds
+__device__ __forceinline__ void tangent_mid(float (&row)[32], const float (&m)[32], const float (&f2)[32], float att, const float *vec) {
+  float dsd = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 w = lds4(vec + vWA * 32 + 4 * k4);
+    const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 4 * k4 + e;
+      row[k] *= f2[k];
+      dsd = fmaf(ww[e], row[k], dsd);
+    }
+  }
+  const float ds = att * (1.0f - att) * dsd;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) row[k] = fmaf(m[k], ds, row[k] * att);
+}
+
+// du = < wc2 * fc, Wc1 dms >
+__device__ __forceinline__ float tangent_du(const float (&acc)[32], const float (&fc)[32], const float *vec) {
+  float du = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 w = lds4(vec + vWC2 * 32 + 4 * k4);
+    const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) du = fmaf(ww[e] * fc[4 * k4 + e], acc[4 * k4 + e], du);
+  }
+  return du;
+}
+
+// row = f1 * (row + c1 dr2 + d1 dea)
+__device__ __forceinline__ void tangent_in(float (&row)[32], const float (&f1)[32], const float *vec, float dr2, float dea) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 c = lds4(vec + vC1 * 32 + 4 * k4);
+    const float4 d = lds4(vec + vD1 * 32 + 4 * k4);
+    const float cc[4] = {c.x, c.y, c.z, c.w}, dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 4 * k4 + e;
+      row[k] = f1[k] * (row[k] + cc[e] * dr2 + dd[e] * dea);
+    }
+  }
+}
+
+// z1 (without the geometric terms) of a layer-0 edge from the class tables:  P0_i + Q0_j
+__device__ __forceinline__ void z1_layer0(float (&row)[32], const float *sCls, float f0i, float f1i, float f0j, float f1j) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 a0 = lds4(sCls + 4 * k4), a1 = lds4(sCls + 32 + 4 * k4), ab = lds4(sCls + 64 + 4 * k4);
+    const float4 b0 = lds4(sCls + 96 + 4 * k4), b1 = lds4(sCls + 128 + 4 * k4), bb = lds4(sCls + 160 + 4 * k4);
+    row[4 * k4 + 0] = fmaf(f0i, a0.x, fmaf(f1i, a1.x, ab.x)) + fmaf(f0j, b0.x, fmaf(f1j, b1.x, bb.x));
+    row[4 * k4 + 1] = fmaf(f0i, a0.y, fmaf(f1i, a1.y, ab.y)) + fmaf(f0j, b0.y, fmaf(f1j, b1.y, bb.y));
+    row[4 * k4 + 2] = fmaf(f0i, a0.z, fmaf(f1i, a1.z, ab.z)) + fmaf(f0j, b0.z, fmaf(f1j, b1.z, bb.z));
+    row[4 * k4 + 3] = fmaf(f0i, a0.w, fmaf(f1i, a1.w, ab.w)) + fmaf(f0j, b0.w, fmaf(f1j, b1.w, bb.w));
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ void node_feats(int node, float tcond, float beta, float &f0, float &f1) {
+  f0 = (2 * node < NP) ? tcond : beta;
+  f1 = (2 * node + 1 < NP) ? tcond : beta;
+}
+
+__device__ __forceinline__ float comp(const float4 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+// sum over the NP rows of the thread's particle of a per-row scalar (all threads of the team call)
+template <int NP, bool SPLIT>
+__device__ __forceinline__ float particle_sum(const Team<SPLIT> &T, float *buf, float v, int p) {
+  T.sync();
+  buf[T.tt] = v;
+  T.sync();
+  float a = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < NP; ++k) a += buf[p * NP + k];
+  return a;
+}
+
+template <int NP, int NTEAM, bool SPLIT>
+__global__ void __launch_bounds__(NTEAM * 128, 1)
+egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restrict__ ht, const float *__restrict__ x,
+                           const float *__restrict__ beta_in, int64_t B, float *__restrict__ score,
+                           float *__restrict__ divergence, float *__restrict__ scratch) {
+  extern __shared__ __align__(16) float sm_raw[];
+  using C = Ctx<NP, NTEAM, SPLIT, true>;
+  using S = Smem<NP, NTEAM, SPLIT, true>;
+  constexpr int PB = C::PB;
+  constexpr int L = 3;
+  const float rng = kCoordsRange / (float)L;
+  C c;
+  uint32_t tmem_base;
+  setup(c, sm_raw, wpack, tmem_base);
+  Team<SPLIT> &T = c.T;
+  const int tt = T.tt;
+  const float *W0 = wpack + pk::kHeader, *W1 = W0 + pk::kLayer, *W2l = W1 + pk::kLayer;
+  float4 *sDX = reinterpret_cast<float4 *>(c.tm + S::tDX);
+  float4 *sCoef = reinterpret_cast<float4 *>(c.tm + S::tCoef);
+  float *sOwnA = c.tm + S::tOwnA, *sOwnB = c.tm + S::tOwnB, *sKP2 = c.tm + S::tKP2, *sKdP2 = c.tm + S::tKdP2;
+  float *scr = scratch ? scratch + ((size_t)blockIdx.x * NTEAM + c.team) * kScrVecs * kRows * 32 + (size_t)tt * 32 : nullptr;
+  auto SCR = [&](int v) { return scr + (size_t)v * kRows * 32; };
+
+  // layer-0 class tables:  A0 e0, A0 e1, A0 eb + b1, B0 e0, B0 e1, B0 eb
+  if (c.tid < 192) {
+    const int v = c.tid >> 5, ch = c.tid & 31;
+    const float *M = W0 + (v < 3 ? pk::A_b : pk::B_b) + ch * 32;
+    const float *e = c.sEmb + (v % 3) * 32;
+    float acc = (v == 2) ? __ldg(W0 + pk::b1 + ch) : 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) acc = fmaf(__ldg(M + k), e[k], acc);
+    c.sCls[v * 32 + ch] = acc;
+  }
+  __syncthreads();
+
+  const int64_t nbatch = (B + (int64_t)NTEAM * PB - 1) / ((int64_t)NTEAM * PB);
+  for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    const int64_t p0 = (batch * NTEAM + c.team) * PB;
+    const bool team_active = p0 < B;
+    const int64_t part = p0 + c.p;
+    const bool ok = c.row_ok && part < B;
+    const int64_t pc = ok ? part : (B - 1);
+    const int ic = c.row_ok ? c.i : 0;
+    const int pp = c.row_ok ? c.p : 0;
+    const float h = __ldg(ht + pc), beta = __ldg(beta_in + pc);
+    const float c_in = rsqrtf(1.0f + h), c_s = 1.0f / (1.0f + h), c_out = sqrtf(h) * c_in, c_noise = 0.125f * logf(h);
+    const float *src = x + pc * 3 * NP + 3 * ic;
+    const float xr0 = __ldg(src), xr1 = __ldg(src + 1), xr2 = __ldg(src + 2);
+    const float4 yi = make_float4(c_in * xr0, c_in * xr1, c_in * xr2, 0.f);
+    c.sX[tt] = yi;
+    primal_forward_rows(c, wpack, c_noise, beta, team_active, divergence ? scr : nullptr);
+
+    // ---- score = ((c_s - 1) x + c_out * remove_mean(x^3 - y)) / h        (score_net.py:21-43)
+    if (team_active) {
+      const float4 xl = c.sX3[tt];
+      const float4 v = make_float4(xl.x - yi.x, xl.y - yi.y, xl.z - yi.z, 0.f);
+      const float4 mean = particle_mean<NP, SPLIT>(T, reinterpret_cast<float4 *>(c.sQb), v, pp);
+      if (ok) {
+        float *dst = score + part * 3 * NP + 3 * c.i;
+        dst[0] = ((c_s * xr0 + c_out * (v.x - mean.x)) - xr0) / h;
+        dst[1] = ((c_s * xr1 + c_out * (v.y - mean.y)) - xr1) / h;
+        dst[2] = ((c_s * xr2 + c_out * (v.z - mean.z)) - xr2) / h;
+      }
+    }
+    if (divergence == nullptr) continue;
+
+    float f0i, f1i;
+    node_feats<NP>(ic, c_noise, beta, f0i, f1i);
+    const float *vec0 = c.vec(0), *vec1 = c.vec(1), *vec2 = c.vec(2);
+    float row[32], f1[32], m[32], f2[32], fc[32];
+
+    // =========================== pre-phase: own-direction layer-0 tangents of every node
+    WeightSrc setA;
+    setA.p[0] = W0 + pk::W2_b; setA.p[1] = W0 + pk::Wc1_b; setA.p[2] = W0 + pk::W3a_b; setA.p[3] = W0 + pk::W4_b;
+    setA.p[4] = W1 + pk::A_b;
+    setA.count = 5;
+    WeightSrc setB;  // B1, then the layer-1 edge set and W3h1
+    setB.p[0] = W1 + pk::B_b; setB.p[1] = W1 + pk::W2_b; setB.p[2] = W1 + pk::Wc1_b; setB.p[3] = W1 + pk::W3a_b;
+    setB.p[4] = W1 + pk::W3h_b;
+    setB.count = 5;
+    WeightSrc setC;  // W4_1, layer-2 node products and edge set
+    setC.p[0] = W1 + pk::W4_b; setC.p[1] = W2l + pk::A_b; setC.p[2] = W2l + pk::B_b; setC.p[3] = W2l + pk::W2_b;
+    setC.p[4] = W2l + pk::Wc1_b;
+    setC.count = 5;
+    load_weights(c, setA);
+    if (team_active) {
+      float dxo[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) dxo[a][b] = (a == b) ? 1.0f : 0.0f;
+#pragma unroll 1
+      for (int u = 0; u < NP - 1; ++u) {
+        const int j = c.sender(u), rj = pp * NP + j;
+        const float4 yj = c.sX[rj];
+        const Geo g = edge_geo4(yi, yj, yi, yj);
+        float f0j, f1j;
+        node_feats<NP>(j, c_noise, beta, f0j, f1j);
+        z1_layer0(row, c.sCls, f0i, f1i, f0j, f1j);
+        stage1<true, false>(row, f1, nullptr, 0, vec0, g.r2, g.ea);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAcc0, 0, false); });
+        T.ld(sAcc0, row);
+        const float att = stage2<true>(row, m, f2, vec0);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAccC, 1, false); });
+        T.ld(sAccC, row);
+        const float th = stage3<true>(row, fc, vec0);
+        const float phi = rng * th, dphi_du = rng * (1.0f - th * th);
+        // base row: d z1 / d r2 (edge_attr == radial in layer 0)
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 cc = lds4(vec0 + vC1 * 32 + 4 * k4), dd = lds4(vec0 + vD1 * 32 + 4 * k4);
+          row[4 * k4] = f1[4 * k4] * (cc.x + dd.x); row[4 * k4 + 1] = f1[4 * k4 + 1] * (cc.y + dd.y);
+          row[4 * k4 + 2] = f1[4 * k4 + 2] * (cc.z + dd.z); row[4 * k4 + 3] = f1[4 * k4 + 3] * (cc.w + dd.w);
+        }
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAcc0, 0, false); });
+        T.ld(sAcc0, row);
+        tangent_mid(row, m, f2, att, vec0);  // wvec
+        T.store_row(row);
+        const float dd3[3] = {g.d0, g.d1, g.d2};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {  // S_a += 2 d_a wvec   (TMEM-resident accumulators)
+          float tmp[32];
+          if (u == 0) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) tmp[k] = 2.0f * dd3[a] * row[k];
+          } else {
+            T.ld(sT0 + a, tmp);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) tmp[k] = fmaf(2.0f * dd3[a], row[k], tmp[k]);
+          }
+          T.st(sT0 + a, tmp);
+        }
+        T.round_trip([&] { T.mma(sAccC, 1, false); });
+        T.ld(sAccC, row);
+        const float du_base = tangent_du(row, fc, vec0);
+        const float k2 = g.inv * g.inv / g.nrm;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float dphi = dphi_du * du_base * 2.0f * dd3[a];
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            const float ddh = ((a == b) ? g.inv : 0.0f) - dd3[b] * dd3[a] * k2;
+            dxo[a][b] += ddh * phi + dd3[b] * g.inv * dphi;
+          }
+        }
+      }
+      // finish: dh1o[a] = W4 (f3^0 * W3a S_a);  piAo = A1 dh1o, piBo = B1 dh1o
+      load_vec_global(SCR(qF30), f1);  // f1 <- f3^0
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        T.ld(sT0 + a, row);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAcc0, 2, false); });
+        T.ld(sAcc0, row);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) row[k] *= f1[k];
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAcc0, 3, false); });
+        T.ld(sAcc0, row);
+        store_vec_global(SCR(qDh1o + a), row);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAccC, 4, false); });
+        T.ld(sAccC, row);
+        store_vec_global(SCR(qPiAo + a), row);
+      }
+      {
+        float *d = SCR(qDxo);
+        *reinterpret_cast<float4 *>(d) = make_float4(dxo[0][0], dxo[0][1], dxo[0][2], 0.f);
+        *reinterpret_cast<float4 *>(d + 4) = make_float4(dxo[1][0], dxo[1][1], dxo[1][2], 0.f);
+        *reinterpret_cast<float4 *>(d + 8) = make_float4(dxo[2][0], dxo[2][1], dxo[2][2], 0.f);
+      }
+      // P^1 back into its TMEM slot for the passes
+      load_vec_global(SCR(qP1), row);
+      T.st(sP, row);
+    }
+    {  // piBo[a] = B1 dh1o[a]
+      WeightSrc sB1;
+      sB1.p[0] = W1 + pk::B_b;
+      sB1.count = 1;
+      load_weights(c, sB1);
+      if (team_active) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          load_vec_global(SCR(qDh1o + a), row);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAcc0, 0, false); });
+          T.ld(sAcc0, row);
+          store_vec_global(SCR(qPiBo + a), row);
+        }
+      }
+    }
+
+    // =========================== passes over the tangent node k
+    float trace = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < NP; ++k) {
+      const bool is_k = c.row_ok && (c.i == k);
+      const int rk = pp * NP + k;
+      float cf[3] = {0.f, 0.f, 0.f};
+      float dxi[3][3];
+      load_weights(c, setA);
+      // ---------------- layer 0: edge (i, k)
+      if (team_active) {
+        const float4 yk = c.sX[rk];
+        const Geo g = edge_geo4(yi, yk, yi, yk);
+        float f0k, f1k;
+        node_feats<NP>(k, c_noise, beta, f0k, f1k);
+        z1_layer0(row, c.sCls, f0i, f1i, f0k, f1k);
+        stage1<true, false>(row, f1, nullptr, 0, vec0, g.r2, g.ea);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAcc0, 0, false); });
+        T.ld(sAcc0, row);
+        const float att = stage2<true>(row, m, f2, vec0);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAccC, 1, false); });
+        T.ld(sAccC, row);
+        const float th = stage3<true>(row, fc, vec0);
+        const float phi = rng * th, dphi_du = rng * (1.0f - th * th);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 cc = lds4(vec0 + vC1 * 32 + 4 * k4), dd = lds4(vec0 + vD1 * 32 + 4 * k4);
+          row[4 * k4] = f1[4 * k4] * (cc.x + dd.x); row[4 * k4 + 1] = f1[4 * k4 + 1] * (cc.y + dd.y);
+          row[4 * k4 + 2] = f1[4 * k4 + 2] * (cc.z + dd.z); row[4 * k4 + 3] = f1[4 * k4 + 3] * (cc.w + dd.w);
+        }
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAcc0, 0, false); });
+        T.ld(sAcc0, row);
+        tangent_mid(row, m, f2, att, vec0);  // wvec_ik
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAccC, 1, false); T.mma(sAcc0, 2, false); });
+        T.ld(sAccC, row);
+        const float du_base = tangent_du(row, fc, vec0);
+        T.ld(sAcc0, row);
+        load_vec_global(SCR(qF30), f1);
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) row[kk] *= f1[kk];
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAcc0, 3, false); });
+        T.ld(sAcc0, row);  // omega_ik
+        store_vec_global(SCR(qOmega), row);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sPA, 4, false); });  // piA_ik = A1 omega -> its TMEM slot (piB follows once B1 is loaded)
+        const float dd3[3] = {g.d0, g.d1, g.d2};
+        if (!is_k) {
+          const float k2 = g.inv * g.inv / g.nrm;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            cf[a] = -2.0f * dd3[a];
+            const float dphi = dphi_du * du_base * cf[a];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+              const float ddh = ((a == b) ? -g.inv : 0.0f) + dd3[b] * dd3[a] * k2;
+              dxi[a][b] = ddh * phi + dd3[b] * g.inv * dphi;
+            }
+          }
+        } else {
+          const float *d = SCR(qDxo);
+          const float4 q0 = *reinterpret_cast<const float4 *>(d), q1 = *reinterpret_cast<const float4 *>(d + 4),
+                       q2 = *reinterpret_cast<const float4 *>(d + 8);
+          dxi[0][0] = q0.x; dxi[0][1] = q0.y; dxi[0][2] = q0.z;
+          dxi[1][0] = q1.x; dxi[1][1] = q1.y; dxi[1][2] = q1.z;
+          dxi[2][0] = q2.x; dxi[2][1] = q2.y; dxi[2][2] = q2.z;
+          // publish the tangent node's own-direction vectors and its P^2
+#pragma unroll 1
+          for (int a = 0; a < 3; ++a) {
+            load_vec_global(SCR(qPiAo + a), row);
+            store_vec_smem(sOwnA + (pp * 3 + a) * 32, row);
+            load_vec_global(SCR(qPiBo + a), row);
+            store_vec_smem(sOwnB + (pp * 3 + a) * 32, row);
+          }
+          load_vec_global(SCR(qP2), row);
+          store_vec_smem(sKP2 + pp * 32, row);
+        }
+        sCoef[tt] = make_float4(cf[0], cf[1], cf[2], 0.f);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) sDX[tt * 3 + a] = make_float4(dxi[a][0], dxi[a][1], dxi[a][2], 0.f);
+      }
+      // ---------------- layer 1 (dense)
+      load_weights(c, setB);
+      if (team_active) {  // piB_ik = B1 omega (the A tile still holds the omega rows)
+        T.round_trip([&] { T.mma(sAcc0, 0, false); });
+        T.ld(sAcc0, row);
+        if (is_k) {
+#pragma unroll
+          for (int kk = 0; kk < 32; ++kk) row[kk] = 0.f;
+        }
+        qrow_store(c.sQb, tt, row);
+        umma::fence_before_thread_sync();
+        T.sync();
+        umma::fence_after_thread_sync();
+      }
+      float dx2[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) dx2[a][b] = dxi[a][b];
+      if (team_active) {
+        const float4 xi = c.sX[kRows + tt];
+#pragma unroll 1
+        for (int u = 0; u < NP - 1; ++u) {
+          const int j = c.sender(u), rj = pp * NP + j;
+          const bool jk = (j == k);
+          const float4 yj = c.sX[rj];
+          const Geo g = edge_geo4(xi, c.sX[kRows + rj], yi, yj);
+          T.ld(sP, row);
+          stage1<true>(row, f1, c.sQa, rj, vec1, g.r2, g.ea);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAcc0, 1, false); });
+          T.ld(sAcc0, row);
+          const float att = stage2<true>(row, m, f2, vec1);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAccC, 2, false); });
+          T.ld(sAccC, row);
+          const float th = stage3<true>(row, fc, vec1);
+          const float phi = rng * th, dphi_du = rng * (1.0f - th * th);
+          const float k2 = g.inv * g.inv / g.nrm;
+          const float4 cfj = sCoef[rj];
+          const float dd3[3] = {g.d0, g.d1, g.d2};
+          const float e03[3] = {yi.x - yj.x, yi.y - yj.y, yi.z - yj.z};
+          const float sgn = (is_k ? 1.0f : 0.0f) - (jk ? 1.0f : 0.0f);
+          const bool accz = u > 0;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const float4 dxj = sDX[rj * 3 + a];
+            const float D0 = dxi[a][0] - dxj.x, D1 = dxi[a][1] - dxj.y, D2 = dxi[a][2] - dxj.z;
+            const float dotD = g.d0 * D0 + g.d1 * D1 + g.d2 * D2;
+            // tangent input  dP_i + dQ_j
+            T.ld(sPA, row);
+            const float cA = cf[a], cB = comp(cfj, a);
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) row[kk] = is_k ? 0.f : cA * row[kk];
+            if (is_k) add_vec(row, sOwnA + (pp * 3 + a) * 32);
+            {
+#pragma unroll
+              for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 q = qrow_ld4(c.sQb, rj, k4);
+                row[4 * k4] = fmaf(cB, q.x, row[4 * k4]); row[4 * k4 + 1] = fmaf(cB, q.y, row[4 * k4 + 1]);
+                row[4 * k4 + 2] = fmaf(cB, q.z, row[4 * k4 + 2]); row[4 * k4 + 3] = fmaf(cB, q.w, row[4 * k4 + 3]);
+              }
+            }
+            if (jk) add_vec(row, sOwnB + (pp * 3 + a) * 32);
+            tangent_in(row, f1, vec1, 2.0f * dotD, 2.0f * sgn * e03[a]);
+            T.store_row(row);
+            T.round_trip([&] { T.mma(sAcc0, 1, false); });
+            T.ld(sAcc0, row);
+            tangent_mid(row, m, f2, att, vec1);
+            T.store_row(row);
+            T.round_trip([&] { T.mma(sAccC, 2, false); T.mma(sT0 + a, 3, accz); });
+            T.ld(sAccC, row);
+            const float dphi = dphi_du * tangent_du(row, fc, vec1);
+            const float cg = dotD * k2;
+            dx2[a][0] += (D0 * g.inv - g.d0 * cg) * phi + g.d0 * g.inv * dphi;
+            dx2[a][1] += (D1 * g.inv - g.d1 * cg) * phi + g.d1 * g.inv * dphi;
+            dx2[a][2] += (D2 * g.inv - g.d2 * cg) * phi + g.d2 * g.inv * dphi;
+          }
+        }
+        // dz3[a] += W3h1 dh^1[a]   (W3h1 sits in slot 4 of this set)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (is_k) {
+            load_vec_global(SCR(qDh1o + a), row);
+          } else {
+            load_vec_global(SCR(qOmega), row);
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) row[kk] *= cf[a];
+          }
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sT0 + a, 4, true); });
+        }
+      }
+      // ---------------- node update of layer 1 on the tangents, then layer 2 on edge (k, i) by the sender's thread
+      load_weights(c, setC);
+      if (team_active) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) sDX[tt * 3 + a] = make_float4(dx2[a][0], dx2[a][1], dx2[a][2], 0.f);
+        umma::fence_before_thread_sync();
+        T.sync();
+        umma::fence_after_thread_sync();
+        const float4 yk = c.sX[rk];
+        const Geo g = edge_geo4(c.sX[2 * kRows + rk], c.sX[2 * kRows + tt], yk, yi);  // d = x_k - x_i (receiver k)
+        load_vec_smem(sKP2 + pp * 32, row);
+        load_vec_global(SCR(qQ2), f1);
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) row[kk] += f1[kk];
+        stage1<true, false>(row, f1, nullptr, 0, vec2, g.r2, g.ea);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAcc0, 3, false); });
+        T.ld(sAcc0, row);
+        const float att = stage2<true>(row, m, f2, vec2);
+        T.store_row(row);
+        T.round_trip([&] { T.mma(sAccC, 4, false); });
+        T.ld(sAccC, row);
+        const float th = stage3<true>(row, fc, vec2);
+        const float phi = rng * th, dphi_du = rng * (1.0f - th * th);
+        const float k2 = g.inv * g.inv / g.nrm;
+        const float dd3[3] = {g.d0, g.d1, g.d2};
+        const float e03[3] = {yk.x - yi.x, yk.y - yi.y, yk.z - yi.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          float tmp[32];
+          T.ld(sT0 + a, row);  // dz3 = W3a dagg (accumulated over the slots) + W3h dh1
+          load_vec_global(SCR(qF31), tmp);
+#pragma unroll
+          for (int kk = 0; kk < 32; ++kk) row[kk] *= tmp[kk];
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAcc0, 0, false); });
+          T.ld(sAcc0, row);
+          if (is_k) {
+            load_vec_global(SCR(qDh1o + a), tmp);
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) row[kk] += tmp[kk];
+          } else {
+            load_vec_global(SCR(qOmega), tmp);
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) row[kk] = fmaf(cf[a], tmp[kk], row[kk]);
+          }
+          T.store_row(row);  // dh^2[a]
+          T.round_trip([&] { T.mma(sAccC, 1, false); T.mma(sAcc0, 2, false); });
+          T.ld(sAccC, tmp);  // (tcgen05.ld is warp-collective: never inside a divergent branch)
+          if (is_k) store_vec_smem(sKdP2 + (pp * 3 + a) * 32, tmp);
+          umma::fence_before_thread_sync();
+          T.sync();
+          umma::fence_after_thread_sync();
+          T.ld(sAcc0, row);  // dQ2_i[a]
+          add_vec(row, sKdP2 + (pp * 3 + a) * 32);
+          const float4 dxk = sDX[rk * 3 + a];
+          const float D0 = dxk.x - dx2[a][0], D1 = dxk.y - dx2[a][1], D2 = dxk.z - dx2[a][2];
+          const float dotD = g.d0 * D0 + g.d1 * D1 + g.d2 * D2;
+          tangent_in(row, f1, vec2, 2.0f * dotD, 2.0f * e03[a]);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAcc0, 3, false); });
+          T.ld(sAcc0, row);
+          tangent_mid(row, m, f2, att, vec2);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAccC, 4, false); });
+          T.ld(sAccC, row);
+          const float dphi = dphi_du * tangent_du(row, fc, vec2);
+          const float Da = (a == 0) ? D0 : ((a == 1) ? D1 : D2);
+          if (is_k) trace += dx2[a][a];
+          else trace += (Da * g.inv - dd3[a] * dotD * k2) * phi + dd3[a] * g.inv * dphi;
+        }
+      }
+    }
+    // ---- div = ((c_s - 1) D + c_out c_in (tr - D)) / h
+    if (team_active) {
+      const float tr = particle_sum<NP, SPLIT>(T, c.tm + S::tRed, c.row_ok ? trace : 0.f, pp);
+      if (ok && c.i == 0) {
+        const float Dn = (float)(3 * NP);
+        divergence[part] = ((c_s - 1.0f) * Dn + c_out * c_in * (tr - Dn)) / h;
+      }
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if ((c.tid >> 5) == 0) umma::tmem_dealloc<512>(tmem_base);
+}
+
+template <int NP, int NTEAM, bool SPLIT>
+static int launch_score_div_rows(const float *w, const float *ht, const float *x, const float *beta, int64_t B, float *sc,
+                                 float *dv, float *scratch, int64_t scratch_bytes, cudaStream_t s) {
+  using S = Smem<NP, NTEAM, SPLIT, true>;
+  auto k = egnn_score_div_rows_kernel<NP, NTEAM, SPLIT>;
+  static_assert(S::kBytes <= 227 * 1024, "shared memory plan exceeds 227 KB");
+  const int64_t need = (int64_t)kNumSMs * NTEAM * kScrVecs * kRows * 32 * 4;
+  PITA_REQUIRE(dv == nullptr || (scratch != nullptr && scratch_bytes >= need), PITA_EINVAL,
+               "egnn_score_div: workspace too small (need %lld bytes)", (long long)need);
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes);
+  if (e != cudaSuccess) { set_error("egnn_score_div_rows_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PITA_ECUDA; }
+  const int64_t nbatch = (B + (int64_t)NTEAM * Shape<NP>::PB - 1) / ((int64_t)NTEAM * Shape<NP>::PB);
+  const unsigned grid = (unsigned)(nbatch < kNumSMs ? nbatch : kNumSMs);
+  k<<<grid, NTEAM * 128, S::kBytes, s>>>(w, ht, x, beta, B, sc, dv, dv ? scratch : nullptr);
+  PITA_CHECK_LAUNCH("egnn_score_div_rows_kernel");
+  return PITA_OK;
+}
+
+}  // namespace rg
+
+int launch_forward_rows(int n, bool split, const float *w, const float *tc, const float *y, const float *beta, int64_t B,
+                        float *vel, cudaStream_t s) {
+  if (n == 13)
+    return split ? rg::launch_forward_rows<13, 2, true>(w, tc, y, beta, B, vel, s)
+                 : rg::launch_forward_rows<13, 2, false>(w, tc, y, beta, B, vel, s);
+  return split ? rg::launch_forward_rows<55, 2, true>(w, tc, y, beta, B, vel, s)
+               : rg::launch_forward_rows<55, 2, false>(w, tc, y, beta, B, vel, s);
+}
+
+int64_t score_div_rows_workspace_bytes(int n) {
+  (void)n;
+  return (int64_t)kNumSMs * 2 * rg::kScrVecs * rg::kRows * 32 * 4;
+}
+
+int launch_score_div_rows(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,
+                          float *sc, float *dv, float *scratch, int64_t scratch_bytes, cudaStream_t s) {
+  if (n == 13)
+    return split ? rg::launch_score_div_rows<13, 2, true>(w, ht, x, beta, B, sc, dv, scratch, scratch_bytes, s)
+                 : rg::launch_score_div_rows<13, 2, false>(w, ht, x, beta, B, sc, dv, scratch, scratch_bytes, s);
+  return split ? rg::launch_score_div_rows<55, 2, true>(w, ht, x, beta, B, sc, dv, scratch, scratch_bytes, s)
+               : rg::launch_score_div_rows<55, 2, false>(w, ht, x, beta, B, sc, dv, scratch, scratch_bytes, s);
+}
+
+}  // namespace pita

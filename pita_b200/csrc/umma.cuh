@@ -75,6 +75,24 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// thread `lane` of the warp writes 32 fp32 values to row (lane_base + lane), columns [col, col+32)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n\t"
+      "tcgen05.wait::st.sync.aligned;" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
@@ -95,16 +113,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
 // ---- writing one K-major operand row (32 fp32 = 128 B) into a SWIZZLE_128B tile whose base is 1024-B aligned.
 // 16-byte chunk j of row r lands at chunk (j ^ (r & 7)).
 __device__ __forceinline__ void store_row_sw128(float *tile, int row, const float (&v)[32]) {
-  float4 *base = reinterpret_cast<float4 *>(tile) + row * 8;
-  const int x = row & 7;
+  const uint32_t base = smem_u32(tile) + (uint32_t)row * 128u;
+  const uint32_t x = (uint32_t)(row & 7);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) base[j ^ x] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  for (uint32_t j = 0; j < 8; ++j)
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((j ^ x) << 4)), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                 "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                 : "memory");
 }
 
-// split an fp32 value into a TF32-representable high part and the fp32 remainder (for 3xTF32)
+// Split an fp32 value into two TF32-representable parts, hi + lo ~= a (for 3xTF32).  Both parts are rounded to
+// nearest (add half an ulp of the 10-bit mantissa, then clear the 13 low bits) instead of being left to the tensor
+// core's truncation: |a - hi - lo| <= 2^-24 |a|, which keeps the three-product sum at plain-fp32 accuracy
+// (measured: truncating splits are ~8x less accurate on the LJ-55 network).
+__device__ __forceinline__ float round_tf32(float a) { return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
-  hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
-  lo = a - hi;
+  hi = round_tf32(a);
+  lo = round_tf32(a - hi);
 }
 
 }  // namespace umma
