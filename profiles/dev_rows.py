@@ -69,6 +69,7 @@ if what == "prof":
     x = O.centre(O.md_shaped_coords(B, n, seed=3) * 1.5, n).cuda()
     ht = torch.full((B,), 2.0, device="cuda"); be = torch.full((B,), 1.0, device="cuda")
     for _ in range(2):
+        ops.egnn_forward(w, 32, 3, n, ht, x, be)
         ops.egnn_score_div(w, 32, 3, n, ht, x, 1.0, mode=mode)
         ops.egnn_energy(w, 32, 3, n, ht, x, be)
     torch.cuda.synchronize()
