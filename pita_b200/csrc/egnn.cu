@@ -1,5 +1,7 @@
 // EGNN denoiser kernels (fp32 SIMT): forward, energy reverse pass, score + divergence (SIMT tangent pass).
 // Shared device code (primal forward, edge evaluation, shared-memory plan) lives in egnn_common.cuh.
+#include <cstdlib>
+#include <cstring>
 #include "egnn_common.cuh"
 
 namespace pita {
@@ -670,6 +672,8 @@ static int check_common(const char *what, const float *w, int hidden, int layers
 namespace pita {
 int launch_forward_rows(int n, bool split, const float *w, const float *tc, const float *y, const float *beta, int64_t B,
                         float *vel, cudaStream_t s);
+int launch_energy_rows(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,
+                       float *e, float *g, float *dh, cudaStream_t s);
 int64_t score_div_rows_workspace_bytes(int n);
 int launch_score_div_rows(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,
                           float *sc, float *dv, float *scratch, int64_t scratch_bytes, cudaStream_t s);
@@ -702,8 +706,12 @@ extern "C" int pita_egnn_energy(const float *wpack, int hidden, int layers, int 
   if (B == 0) return PITA_OK;
   PITA_REQUIRE(energy, PITA_EINVAL, "egnn_energy: null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return n == 13 ? launch_energy<13, 13>(wpack, ht, x, beta, B, energy, grad_x, dE_dh, s)
-                 : launch_energy<55, 11>(wpack, ht, x, beta, B, energy, grad_x, dE_dh, s);
+  // PITA_ENERGY_ENGINE=simt selects the fp32 CUDA-core kernel (kept for A/B checks); default: tcgen05 row engine, 3xTF32
+  static const bool simt = [] { const char *v = getenv("PITA_ENERGY_ENGINE"); return v && strcmp(v, "simt") == 0; }();
+  if (simt)
+    return n == 13 ? launch_energy<13, 13>(wpack, ht, x, beta, B, energy, grad_x, dE_dh, s)
+                   : launch_energy<55, 11>(wpack, ht, x, beta, B, energy, grad_x, dE_dh, s);
+  return launch_energy_rows(n, true, wpack, ht, x, beta, B, energy, grad_x, dE_dh, s);
 }
 
 
@@ -724,6 +732,11 @@ extern "C" int pita_egnn_score_div(const float *wpack, int hidden, int layers, i
   if (mode == PITA_DIV_FP32)
     return n == 13 ? launch_score<13, 13, 2>(wpack, ht, x, beta, B, score, div, s)
                    : launch_score<55, 11, 2>(wpack, ht, x, beta, B, score, div, s);
-  return launch_score_div_rows(n, mode == PITA_DIV_3XTF32, wpack, ht, x, beta, B, score, div, static_cast<float *>(workspace),
-                               workspace_bytes, s);
+  if (mode == PITA_DIV_TF32 && div != nullptr) {
+    // plain-TF32 tangents for the divergence only: the score itself is always evaluated at fp32 accuracy (3xTF32)
+    rc = launch_score_div_rows(n, false, wpack, ht, x, beta, B, score, div, static_cast<float *>(workspace), workspace_bytes, s);
+    if (rc) return rc;
+    return launch_score_div_rows(n, true, wpack, ht, x, beta, B, score, nullptr, nullptr, 0, s);
+  }
+  return launch_score_div_rows(n, true, wpack, ht, x, beta, B, score, div, static_cast<float *>(workspace), workspace_bytes, s);
 }

@@ -9,6 +9,8 @@ namespace rg {
 
 // TMEM column slots (32 columns each) of one team
 enum Slot { sAcc0 = 0, sAccC = 1, sT0 = 2, sT1 = 3, sT2 = 4, sP = 5, sPA = 6, sH = 7, kSlots = 8 };
+// energy (reverse) kernel: the tangent accumulators sT1/sT2/sPA are free and hold per-row state of the reverse pass
+enum RevSlot { sGAgg = sT0, sF30 = sT1, sF31 = sT2, sH1 = sPA, sGH = sH };
 // weight slots
 enum WSlot { wA = 0, wB = 1, wW2 = 2, wWc1 = 3, wW3a = 4 };
 
@@ -19,8 +21,11 @@ struct Shape {
 };
 
 // ---- shared-memory plan -------------------------------------------------------------------------
-template <int NP, int NTEAM, bool SPLIT, bool TANGENT>
+// MODE: 0 = plain forward, 1 = score + divergence (tangent regions), 2 = energy (reverse-pass scatter regions)
+constexpr int kModeFwd = 0, kModeTan = 1, kModeRev = 2;
+template <int NP, int NTEAM, bool SPLIT, int MODE>
 struct Smem {
+  static constexpr bool TANGENT = (MODE == kModeTan);
   static constexpr int PB = Shape<NP>::PB;
   // byte offsets from a 1024-aligned base
   static constexpr size_t oW = 0;
@@ -44,7 +49,10 @@ struct Smem {
   static constexpr int tOwnB = tOwnA + (TANGENT ? PB * 96 : 0);   // [PB][3][32]   B1 dh1 of the tangent node
   static constexpr int tKP2 = tOwnB + (TANGENT ? PB * 96 : 0);    // [PB][32]      P2 of the tangent node
   static constexpr int tRed = tKP2 + (TANGENT ? PB * 32 : 0);     // [128]         per-particle reductions
-  static constexpr int kTeamFloats = ((tRed + kRows + 3) / 4) * 4;
+  static constexpr int tGX = tRed + kRows;                        // MODE 2: [128] float4 scatter target, coordinate cotangents
+  static constexpr int tGX0 = tGX + (MODE == kModeRev ? kRows * 4 : 0);   // [128] float4 scatter target, edge_attr path
+  static constexpr int tMean = tGX0 + (MODE == kModeRev ? kRows * 4 : 0); // [128] float4 scratch of particle_mean
+  static constexpr int kTeamFloats = ((tMean + (MODE == kModeRev ? kRows * 4 : 0) + 3) / 4) * 4;
   static constexpr size_t kBytes = 1024 + oF + (size_t)(fTeam + NTEAM * kTeamFloats) * 4;
 };
 
@@ -126,9 +134,9 @@ __device__ __forceinline__ void add_vec(float (&row)[32], const float *vec32) {
 }
 
 // ---- common context --------------------------------------------------------------------------------
-template <int NP, int NTEAM, bool SPLIT, bool TANGENT>
+template <int NP, int NTEAM, bool SPLIT, int MODE>
 struct Ctx {
-  using S = Smem<NP, NTEAM, SPLIT, TANGENT>;
+  using S = Smem<NP, NTEAM, SPLIT, MODE>;
   static constexpr int PB = Shape<NP>::PB;
   static constexpr int R = Shape<NP>::R;
   Team<SPLIT> T;
@@ -143,10 +151,10 @@ struct Ctx {
 };
 
 // One-time CTA setup: carve shared memory, TMEM, mbarriers, per-layer vectors.
-template <int NP, int NTEAM, bool SPLIT, bool TANGENT>
-__device__ __forceinline__ void setup(Ctx<NP, NTEAM, SPLIT, TANGENT> &c, float *sm_raw, const float *__restrict__ wpack,
+template <int NP, int NTEAM, bool SPLIT, int MODE>
+__device__ __forceinline__ void setup(Ctx<NP, NTEAM, SPLIT, MODE> &c, float *sm_raw, const float *__restrict__ wpack,
                                       uint32_t &tmem_base_out) {
-  using S = Smem<NP, NTEAM, SPLIT, TANGENT>;
+  using S = Smem<NP, NTEAM, SPLIT, MODE>;
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
   c.tid = threadIdx.x;
   c.team = c.tid >> 7;
@@ -195,8 +203,8 @@ __device__ __forceinline__ void setup(Ctx<NP, NTEAM, SPLIT, TANGENT> &c, float *
   c.T.issuer = uniform32((uint32_t)(warp & 3)) == 0u;
 }
 
-template <int NP, int NTEAM, bool SPLIT, bool TANGENT>
-__device__ __forceinline__ void load_weights(Ctx<NP, NTEAM, SPLIT, TANGENT> &c, const WeightSrc &src) {
+template <int NP, int NTEAM, bool SPLIT, int MODE>
+__device__ __forceinline__ void load_weights(Ctx<NP, NTEAM, SPLIT, MODE> &c, const WeightSrc &src) {
   __syncthreads();  // every team is done with the MMAs that read the old tiles
   load_weight_tiles<SPLIT>(c.wsm, src, c.tid, NTEAM * 128);
   umma::fence_before_thread_sync();
@@ -225,9 +233,10 @@ __device__ __forceinline__ void embed(float (&h)[32], const float *sEmb, int i, 
 //   in : sX[0] = network input coordinates (published, team-synced by the caller), tcond/beta of the thread's particle
 //   out: sX[1..3]; TMEM sP = P^1 (+b1) if KEEP_L1; sQa = Q^1.  When `scratch` != nullptr the per-row vectors the
 //        tangent passes need later are written there: f3^0, f3^1 (silu'(z3)), P^2 (+b1), Q^2   (own-row layout).
-template <int NP, int NTEAM, bool SPLIT, bool TANGENT>
-__device__ __forceinline__ void primal_forward_rows(Ctx<NP, NTEAM, SPLIT, TANGENT> &c, const float *__restrict__ wpack,
+template <int NP, int NTEAM, bool SPLIT, int MODE>
+__device__ __forceinline__ void primal_forward_rows(Ctx<NP, NTEAM, SPLIT, MODE> &c, const float *__restrict__ wpack,
                                                     float tcond, float beta, bool team_active, float *scratch_row) {
+  constexpr bool TANGENT = (MODE == kModeTan);
   constexpr int L = 3;
   const float rng = kCoordsRange / (float)L;
   Team<SPLIT> &T = c.T;
@@ -307,6 +316,11 @@ __device__ __forceinline__ void primal_forward_rows(Ctx<NP, NTEAM, SPLIT, TANGEN
 #pragma unroll
           for (int k = 0; k < 32; ++k) { float a; silu_both(row[k], a, f3[k]); row[k] = a; }
           store_vec_global(scratch_row + l * kRows * 32, f3);  // f3^l
+        } else if (MODE == kModeRev) {  // the reverse pass keeps f3^l in its own TMEM lane
+          float f3[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) { float a; silu_both(row[k], a, f3[k]); row[k] = a; }
+          T.st(sF30 + l, f3);
         } else {
 #pragma unroll
           for (int k = 0; k < 32; ++k) row[k] = silu_val(row[k]);
@@ -320,6 +334,7 @@ __device__ __forceinline__ void primal_forward_rows(Ctx<NP, NTEAM, SPLIT, TANGEN
 #pragma unroll
         for (int k = 0; k < 32; ++k) hh[k] += row[k];
         T.st(sH, hh);
+        if (MODE == kModeRev && l == 0) T.st(sH1, hh);  // h^1 is needed again to rebuild P^1, Q^1
       }
     }
   }
@@ -346,6 +361,18 @@ __device__ __forceinline__ float4 particle_mean(const Team<SPLIT> &T, float4 *bu
   return make_float4(a / NP, b / NP, cc / NP, 0.f);
 }
 
+// sum over the NP rows of the thread's particle of a per-row scalar (all threads of the team call)
+template <int NP, bool SPLIT>
+__device__ __forceinline__ float particle_sum(const Team<SPLIT> &T, float *buf, float v, int p) {
+  T.sync();
+  buf[T.tt] = v;
+  T.sync();
+  float a = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < NP; ++k) a += buf[p * NP + k];
+  return a;
+}
+
 // ================================================================================================
 // Kernel: plain forward   vel = EGNN_dynamics(tcond, y, beta)
 // ================================================================================================
@@ -354,7 +381,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
 egnn_forward_rows_kernel(const float *__restrict__ wpack, const float *__restrict__ tcond, const float *__restrict__ y,
                          const float *__restrict__ beta, int64_t B, float *__restrict__ vel) {
   extern __shared__ __align__(16) float sm_raw[];
-  using C = Ctx<NP, NTEAM, SPLIT, false>;
+  using C = Ctx<NP, NTEAM, SPLIT, kModeFwd>;
   C c;
   uint32_t tmem_base;
   setup(c, sm_raw, wpack, tmem_base);
@@ -390,7 +417,7 @@ egnn_forward_rows_kernel(const float *__restrict__ wpack, const float *__restric
 template <int NP, int NTEAM, bool SPLIT>
 static int launch_forward_rows(const float *w, const float *tc, const float *y, const float *beta, int64_t B, float *vel,
                                cudaStream_t s) {
-  using S = Smem<NP, NTEAM, SPLIT, false>;
+  using S = Smem<NP, NTEAM, SPLIT, kModeFwd>;
   auto k = egnn_forward_rows_kernel<NP, NTEAM, SPLIT>;
   static_assert(S::kBytes <= 227 * 1024, "shared memory plan exceeds 227 KB");
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes);
@@ -399,6 +426,273 @@ static int launch_forward_rows(const float *w, const float *tc, const float *y, 
   const unsigned grid = (unsigned)(nbatch < kNumSMs ? nbatch : kNumSMs);
   k<<<grid, NTEAM * 128, S::kBytes, s>>>(w, tc, y, beta, B, vel);
   PITA_CHECK_LAUNCH("egnn_forward_rows_kernel");
+  return PITA_OK;
+}
+
+
+// ================================================================================================
+// Kernel: energy net — E, grad_x E, dE/dh (energy_net.py:14-62) by a hand-derived reverse pass on the row engine.
+// Algebra: oracle/egnn_analytic.py::u_theta_backward / energy_terms.
+//   forward : primal_forward_rows keeps x^0..x^3 (shared), f3^0, f3^1, h^1 (TMEM lanes), P^2 (TMEM) and Q^2 (shared).
+//   reverse : per layer l = 2,1,0 and sender slot u the edge (i, j) is re-evaluated (2 MMAs), its cotangent goes
+//             back through Wc1^T and W2^T (2 MMAs); receiver-side sums stay in the thread, sender-side sums
+//             (B^T path, coordinates) are scattered to the sender's shared-memory row — a slot is a bijection
+//             i -> j inside every particle, so the read-modify-write needs no atomics and is deterministic.
+// ================================================================================================
+template <int NP, int NTEAM, bool SPLIT>
+__global__ void __launch_bounds__(NTEAM * 128, 1)
+egnn_energy_rows_kernel(const float *__restrict__ wpack, const float *__restrict__ ht, const float *__restrict__ x,
+                        const float *__restrict__ beta_in, int64_t B, float *__restrict__ energy,
+                        float *__restrict__ grad_x, float *__restrict__ dE_dh) {
+  extern __shared__ __align__(16) float sm_raw[];
+  using C = Ctx<NP, NTEAM, SPLIT, kModeRev>;
+  using S = Smem<NP, NTEAM, SPLIT, kModeRev>;
+  constexpr int PB = C::PB;
+  constexpr int L = 3;
+  const float rng = kCoordsRange / (float)L;
+  C c;
+  uint32_t tmem_base;
+  setup(c, sm_raw, wpack, tmem_base);
+  Team<SPLIT> &T = c.T;
+  const int tt = T.tt;
+  float *sGQ = c.sQa;  // free once the forward is done (Q^1 is rebuilt from h^1)
+  float4 *sGX = reinterpret_cast<float4 *>(c.tm + S::tGX);
+  float4 *sGX0 = reinterpret_cast<float4 *>(c.tm + S::tGX0);
+  float4 *sMean = reinterpret_cast<float4 *>(c.tm + S::tMean);
+  float *sRed = c.tm + S::tRed;
+  const bool want_grad = (grad_x != nullptr) || (dE_dh != nullptr);
+
+  const int64_t nbatch = (B + (int64_t)NTEAM * PB - 1) / ((int64_t)NTEAM * PB);
+  for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    const int64_t p0 = (batch * NTEAM + c.team) * PB;
+    const bool team_active = p0 < B;
+    const int64_t part = p0 + c.p;
+    const bool ok = c.row_ok && part < B;
+    const int64_t pc = ok ? part : (B - 1);
+    const int ic = c.row_ok ? c.i : 0;
+    const int pp = c.row_ok ? c.p : 0;
+    const float h = __ldg(ht + pc), beta = __ldg(beta_in + pc);
+    const float c_in = rsqrtf(1.0f + h), c_noise = 0.125f * logf(h), rs_h = rsqrtf(h);
+    const float *src = x + pc * 3 * NP + 3 * ic;
+    const float xr[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+    const float4 yi = make_float4(c_in * xr[0], c_in * xr[1], c_in * xr[2], 0.f);
+    c.sX[tt] = yi;
+    primal_forward_rows(c, wpack, c_noise, beta, team_active, nullptr);
+
+    // ---- U = <remove_mean(x^3 - y), y>,  E = |x|^2 / (2 (1 + h)) - U / sqrt(h)        (energy_net.py:29-39)
+    float4 vi = make_float4(0.f, 0.f, 0.f, 0.f), vmean = vi, ymean = vi;
+    float U = 0.f, x2 = 0.f;
+    if (team_active) {
+      const float4 xl = c.sX3[tt];
+      vi = make_float4(xl.x - yi.x, xl.y - yi.y, xl.z - yi.z, 0.f);
+      vmean = particle_mean<NP, SPLIT>(T, sMean, vi, pp);
+      ymean = particle_mean<NP, SPLIT>(T, sMean, yi, pp);
+      const float ui = c.row_ok ? (vi.x - vmean.x) * yi.x + (vi.y - vmean.y) * yi.y + (vi.z - vmean.z) * yi.z : 0.f;
+      const float y2i = c.row_ok ? yi.x * yi.x + yi.y * yi.y + yi.z * yi.z : 0.f;
+      U = particle_sum<NP, SPLIT>(T, sRed, ui, pp);
+      x2 = particle_sum<NP, SPLIT>(T, sRed, y2i, pp) * (1.0f + h);  // |x|^2 = |y|^2 / c_in^2
+      if (ok && c.i == 0) energy[part] = x2 / (2.0f * (1.0f + h)) - rs_h * U;
+    }
+    if (!want_grad) continue;
+
+    // ---- reverse pass.  Cotangent on x^3 is w_i = y_i - mean(y); on h^3 it is 0.
+    float gx[3] = {yi.x - ymean.x, yi.y - ymean.y, yi.z - ymean.z};
+    float g0[3] = {0.f, 0.f, 0.f};  // own part of the cotangent that reaches y through edge_attr
+    float row[32], f1[32], m[32], f2[32], fc[32], gp[32];
+    if (team_active) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) row[k] = 0.f;
+      T.st(sGH, row);
+      T.st(sGAgg, row);
+      qrow_store(sGQ, tt, row);
+      sGX[tt] = make_float4(0.f, 0.f, 0.f, 0.f);
+      sGX0[tt] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll 1
+    for (int l = L - 1; l >= 0; --l) {
+      const float *Wl = wpack + pk::kHeader + l * pk::kLayer;
+      const float *vec = c.vec(l);
+      if (l < L - 1) {
+        // ---- node-MLP reverse: gz3 = f3 * (W4^T gh);  gh += W3h^T gz3;  gagg = W3a^T gz3;  then rebuild P^l, Q^l
+        WeightSrc sN;
+        sN.p[0] = Wl + pk::W4_f; sN.p[1] = Wl + pk::W3h_f; sN.p[2] = Wl + pk::W3a_f; sN.p[3] = Wl + pk::A_b; sN.p[4] = Wl + pk::B_b;
+        sN.count = 5;
+        load_weights(c, sN);
+        if (team_active) {
+          T.ld(sGH, row);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAcc0, 0, false); });
+          T.ld(sAcc0, row);
+          T.ld(sF30 + l, f1);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) row[k] *= f1[k];
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sGH, 1, true); T.mma(sGAgg, 2, false); });
+          if (l == 1) T.ld(sH1, row);
+          else embed<NP>(row, c.sEmb, c.i, c_noise, beta);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sP, 3, false); T.mma(sAcc0, 4, false); });
+          T.ld(sAcc0, row);
+          qrow_store(c.sQb, tt, row);
+          T.ld(sP, row);
+          add_vec(row, vec + vB1 * 32);
+          T.st(sP, row);
+        }
+      }
+      WeightSrc sE;
+      sE.p[0] = Wl + pk::W2_b; sE.p[1] = Wl + pk::Wc1_b; sE.p[2] = Wl + pk::Wc1_f; sE.p[3] = Wl + pk::W2_f; sE.p[4] = Wl + pk::A_f;
+      sE.count = 5;
+      load_weights(c, sE);  // (its barriers also publish the Q rows / zeroed scatter rows to the team)
+      if (team_active) {
+        const float4 xi = c.sX[l * kRows + tt];
+        float gxi[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 32; ++k) gp[k] = 0.f;
+#pragma unroll 1
+        for (int u = 0; u < NP - 1; ++u) {
+          const int rj = pp * NP + c.sender(u);
+          const float4 yj = c.sX[rj];
+          const Geo g = edge_geo4(xi, c.sX[l * kRows + rj], yi, yj);
+          T.ld(sP, row);
+          stage1<true>(row, f1, c.sQb, rj, vec, g.r2, g.ea);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAcc0, 0, false); });
+          T.ld(sAcc0, row);
+          const float att = stage2<true>(row, m, f2, vec);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAccC, 1, false); });
+          T.ld(sAccC, row);
+          const float th = stage3<true>(row, fc, vec);
+          const float phi = rng * th;
+          // coordinate branch cotangent:  gu = <gx, dhat> * range * (1 - th^2);  gzc = gu * wc2 * fc
+          const float gdot = gx[0] * g.d0 + gx[1] * g.d1 + gx[2] * g.d2;
+          const float gu = gdot * g.inv * rng * (1.0f - th * th);
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 w = lds4(vec + vWC2 * 32 + 4 * k4);
+            row[4 * k4] = gu * w.x * fc[4 * k4]; row[4 * k4 + 1] = gu * w.y * fc[4 * k4 + 1];
+            row[4 * k4 + 2] = gu * w.z * fc[4 * k4 + 2]; row[4 * k4 + 3] = gu * w.w * fc[4 * k4 + 3];
+          }
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAcc0, 2, false); });
+          T.ld(sAcc0, row);
+          T.ld(sGAgg, fc);  // (fc is dead: reuse its registers for gagg)
+          float gs = 0.f;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) { row[k] += fc[k]; gs = fmaf(row[k], m[k], gs); }  // gms, gs = <gms, m>
+          const float ga = gs * att * (1.0f - att);
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 w = lds4(vec + vWA * 32 + 4 * k4);
+            row[4 * k4] = fmaf(row[4 * k4], att, w.x * ga) * f2[4 * k4];
+            row[4 * k4 + 1] = fmaf(row[4 * k4 + 1], att, w.y * ga) * f2[4 * k4 + 1];
+            row[4 * k4 + 2] = fmaf(row[4 * k4 + 2], att, w.z * ga) * f2[4 * k4 + 2];
+            row[4 * k4 + 3] = fmaf(row[4 * k4 + 3], att, w.w * ga) * f2[4 * k4 + 3];
+          }
+          T.store_row(row);  // gz2
+          T.round_trip([&] { T.mma(sAcc0, 3, false); });
+          T.ld(sAcc0, row);
+          float gr2 = 0.f, gea = 0.f;
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 cc = lds4(vec + vC1 * 32 + 4 * k4), dd = lds4(vec + vD1 * 32 + 4 * k4);
+            const float c4[4] = {cc.x, cc.y, cc.z, cc.w}, d4[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int k = 4 * k4 + e;
+              row[k] *= f1[k];  // gz1
+              gp[k] += row[k];
+              gr2 = fmaf(c4[e], row[k], gr2);
+              gea = fmaf(d4[e], row[k], gea);
+            }
+          }
+          // sender-side sums: gq_j += gz1   (rows beyond the last whole particle of the tile must not scatter)
+#pragma unroll
+          for (int k4 = 0; k4 < 8 && c.row_ok; ++k4) {
+            float *q = sGQ + rj * 32 + ((k4 ^ (rj & 7)) << 2);
+            const float4 o = lds4(q);
+            sts4(q, make_float4(o.x + row[4 * k4], o.y + row[4 * k4 + 1], o.z + row[4 * k4 + 2], o.w + row[4 * k4 + 3]));
+          }
+          // geometry: d/d(delta) through dhat = delta / (nrm + 1) (times phi) and through r2; edge_attr path on y
+          const float k2 = gdot * phi * g.inv * g.inv / g.nrm;
+          const float a0 = gx[0] * phi * g.inv - g.d0 * k2 + 2.0f * g.d0 * gr2;
+          const float a1 = gx[1] * phi * g.inv - g.d1 * k2 + 2.0f * g.d1 * gr2;
+          const float a2 = gx[2] * phi * g.inv - g.d2 * k2 + 2.0f * g.d2 * gr2;
+          gxi[0] += a0; gxi[1] += a1; gxi[2] += a2;
+          const float e0 = 2.0f * (yi.x - yj.x) * gea, e1 = 2.0f * (yi.y - yj.y) * gea, e2 = 2.0f * (yi.z - yj.z) * gea;
+          g0[0] += e0; g0[1] += e1; g0[2] += e2;
+          if (c.row_ok) {
+            const float4 oa = sGX[rj], ob = sGX0[rj];
+            sGX[rj] = make_float4(oa.x - a0, oa.y - a1, oa.z - a2, 0.f);
+            sGX0[rj] = make_float4(ob.x - e0, ob.y - e1, ob.z - e2, 0.f);
+          }
+        }
+        // ---- combine: gh += A^T gp (+ B^T gq below);  gx += own + scattered parts
+        T.store_row(gp);
+        T.round_trip([&] { T.mma(sGH, 4, true); });  // (its team barrier orders the last scatter before the reads below)
+        qrow_load(sGQ, tt, row);
+        const float4 sc = sGX[tt];
+        gx[0] += gxi[0] + sc.x; gx[1] += gxi[1] + sc.y; gx[2] += gxi[2] + sc.z;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) f1[k] = 0.f;
+        qrow_store(sGQ, tt, f1);
+        sGX[tt] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      WeightSrc sB;
+      sB.p[0] = Wl + pk::B_f;
+      sB.count = 1;
+      load_weights(c, sB);
+      if (team_active) {
+        T.store_row(row);  // gq
+        T.round_trip([&] { T.mma(sGH, 0, true); });
+      }
+    }
+
+    // ---- outputs: dU/dy_i = vel_i - w_i + gx_i + g0_i;  dU/dtcond = sum_i <gh^0_i, d h^0_i / d tcond>
+    if (team_active) {
+      const float4 s0 = sGX0[tt];
+      const float dUdy[3] = {(vi.x - vmean.x) - (yi.x - ymean.x) + gx[0] + g0[0] + s0.x,
+                             (vi.y - vmean.y) - (yi.y - ymean.y) + gx[1] + g0[1] + s0.y,
+                             (vi.z - vmean.z) - (yi.z - ymean.z) + gx[2] + g0[2] + s0.z};
+      float dot_i = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        dot_i = fmaf(dUdy[k], xr[k], dot_i);
+        if (ok && grad_x) grad_x[part * 3 * NP + 3 * c.i + k] = xr[k] / (1.0f + h) - rs_h * c_in * dUdy[k];
+      }
+      float dt_i = 0.f;
+      if (dE_dh != nullptr) {
+        T.ld(sGH, row);
+        const float t0 = (2 * ic < NP) ? 1.0f : 0.0f, t1 = (2 * ic + 1 < NP) ? 1.0f : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) dt_i = fmaf(row[k], t0 * c.sEmb[k] + t1 * c.sEmb[32 + k], dt_i);
+        const float dUdc = particle_sum<NP, SPLIT>(T, sRed, c.row_ok ? dt_i : 0.f, pp);
+        const float dot = particle_sum<NP, SPLIT>(T, sRed, c.row_ok ? dot_i : 0.f, pp);
+        if (ok && c.i == 0) {
+          const float op = 1.0f + h;
+          const float dU_dh = dUdc / (8.0f * h) + dot * (-0.5f) * rsqrtf(op) / op;
+          dE_dh[part] = -x2 / (2.0f * op * op) + 0.5f * rs_h / h * U - rs_h * dU_dh;
+        }
+      }
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if ((c.tid >> 5) == 0) umma::tmem_dealloc<512>(tmem_base);
+}
+
+template <int NP, int NTEAM, bool SPLIT>
+static int launch_energy_rows(const float *w, const float *ht, const float *x, const float *beta, int64_t B, float *e, float *g,
+                              float *dh, cudaStream_t s) {
+  using S = Smem<NP, NTEAM, SPLIT, kModeRev>;
+  auto k = egnn_energy_rows_kernel<NP, NTEAM, SPLIT>;
+  static_assert(S::kBytes <= 227 * 1024, "shared memory plan exceeds 227 KB");
+  cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes);
+  if (err != cudaSuccess) { set_error("egnn_energy_rows_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return PITA_ECUDA; }
+  const int64_t nbatch = (B + (int64_t)NTEAM * Shape<NP>::PB - 1) / ((int64_t)NTEAM * Shape<NP>::PB);
+  const unsigned grid = (unsigned)(nbatch < kNumSMs ? nbatch : kNumSMs);
+  k<<<grid, NTEAM * 128, S::kBytes, s>>>(w, ht, x, beta, B, e, g, dh);
+  PITA_CHECK_LAUNCH("egnn_energy_rows_kernel");
   return PITA_OK;
 }
 
@@ -486,17 +780,6 @@ __device__ __forceinline__ void node_feats(int node, float tcond, float beta, fl
 
 __device__ __forceinline__ float comp(const float4 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
 
-// sum over the NP rows of the thread's particle of a per-row scalar (all threads of the team call)
-template <int NP, bool SPLIT>
-__device__ __forceinline__ float particle_sum(const Team<SPLIT> &T, float *buf, float v, int p) {
-  T.sync();
-  buf[T.tt] = v;
-  T.sync();
-  float a = 0.f;
-#pragma unroll 1
-  for (int k = 0; k < NP; ++k) a += buf[p * NP + k];
-  return a;
-}
 
 template <int NP, int NTEAM, bool SPLIT>
 __global__ void __launch_bounds__(NTEAM * 128, 1)
@@ -504,8 +787,8 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
                            const float *__restrict__ beta_in, int64_t B, float *__restrict__ score,
                            float *__restrict__ divergence, float *__restrict__ scratch) {
   extern __shared__ __align__(16) float sm_raw[];
-  using C = Ctx<NP, NTEAM, SPLIT, true>;
-  using S = Smem<NP, NTEAM, SPLIT, true>;
+  using C = Ctx<NP, NTEAM, SPLIT, kModeTan>;
+  using S = Smem<NP, NTEAM, SPLIT, kModeTan>;
   constexpr int PB = C::PB;
   constexpr int L = 3;
   const float rng = kCoordsRange / (float)L;
@@ -961,7 +1244,7 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
 template <int NP, int NTEAM, bool SPLIT>
 static int launch_score_div_rows(const float *w, const float *ht, const float *x, const float *beta, int64_t B, float *sc,
                                  float *dv, float *scratch, int64_t scratch_bytes, cudaStream_t s) {
-  using S = Smem<NP, NTEAM, SPLIT, true>;
+  using S = Smem<NP, NTEAM, SPLIT, kModeTan>;
   auto k = egnn_score_div_rows_kernel<NP, NTEAM, SPLIT>;
   static_assert(S::kBytes <= 227 * 1024, "shared memory plan exceeds 227 KB");
   const int64_t need = (int64_t)kNumSMs * NTEAM * kScrVecs * kRows * 32 * 4;
@@ -985,6 +1268,15 @@ int launch_forward_rows(int n, bool split, const float *w, const float *tc, cons
                  : rg::launch_forward_rows<13, 2, false>(w, tc, y, beta, B, vel, s);
   return split ? rg::launch_forward_rows<55, 2, true>(w, tc, y, beta, B, vel, s)
                : rg::launch_forward_rows<55, 2, false>(w, tc, y, beta, B, vel, s);
+}
+
+int launch_energy_rows(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,
+                       float *e, float *g, float *dh, cudaStream_t s) {
+  if (n == 13)
+    return split ? rg::launch_energy_rows<13, 2, true>(w, ht, x, beta, B, e, g, dh, s)
+                 : rg::launch_energy_rows<13, 2, false>(w, ht, x, beta, B, e, g, dh, s);
+  return split ? rg::launch_energy_rows<55, 2, true>(w, ht, x, beta, B, e, g, dh, s)
+               : rg::launch_energy_rows<55, 2, false>(w, ht, x, beta, B, e, g, dh, s);
 }
 
 int64_t score_div_rows_workspace_bytes(int n) {
