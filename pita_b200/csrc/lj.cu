@@ -6,6 +6,8 @@
 // with warp shuffles, forces leave through shared memory as coalesced float4 stores.
 //
 // Algorithmic work per configuration: n(n-1)/2 * 31 + 15n FLOP, 24n + 4 bytes.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pita {
@@ -123,6 +125,270 @@ lj_energy_force_kernel(const float *__restrict__ x, int64_t B, float inv_T, floa
   }
 }
 
+
+// =============================================================================================================
+// "Paired" kernel (default): every UNORDERED pair is evaluated once and its force applied to both atoms
+// (Newton's third law), in packed fp32 (FFMA2 / FADD2 / FMUL2: two pairs per instruction, the only way sm_100a
+// reaches its FP32 peak -- profiles/ubench).  18 packed instructions + 2 MUFU.RCP per two pairs
+// => 31 algorithmic FLOP in 9 FMA-pipe issue slots (scalar ordered-pair kernel above: 32 slots).
+//
+// Mapping: lane = configuration (32 configurations per warp-set), warp = atom group g (G groups of S = NA/G atoms).
+// Thread (c, g) keeps its S atoms and their force accumulators in registers and streams atoms b = gS + t,
+// t = 1 .. S-1+K (K = (NA-1)/2, circulant half-neighbourhood: atom a pairs with a+1 .. a+K mod NA, which covers
+// every unordered pair exactly once for odd NA) from shared memory two at a time; the pair (a = gS + r, b) is
+// evaluated iff 1 <= t - r <= K (static after unrolling; a half-valid packed pair is neutralised by adding 1e30
+// to that half's squared distance).  Reactions on b leave through shared memory "slots" q = (t-1)/S: for a fixed
+// slot every atom has exactly one writer, so there are no atomics and the summation order is fixed (deterministic).
+// =============================================================================================================
+struct f2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ f2 pk2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(f2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+
+template <int NA, int G, int CW>
+struct LJPairCfg {
+  static_assert(NA % 2 == 1 && NA % G == 0, "circulant pairing needs an odd atom count split into equal groups");
+  static constexpr int S = NA / G;            // atoms owned by a thread
+  static constexpr int K = (NA - 1) / 2;      // partners per atom
+  static constexpr int T = S - 1 + K;         // streamed atoms per thread
+  static constexpr int QMAX = T / S;          // streamed atom t belongs to group g + t/S; its reaction goes to slot t/S
+  static constexpr int RLAST = T - QMAX * S + 1;  // atoms per group touched in the last (partial) slot
+  static constexpr int CPB = 32 * CW;         // configurations per CTA
+  static constexpr int kThreads = 32 * G * CW;
+  static constexpr int kPosBytes = CPB * NA * 12;
+  // slot q (1 <= q <= QMAX, q % G != 0) holds one reaction vector per (configuration, atom); the last slot only RLAST atoms
+  // per group.  Slots with q % G == 0 target the thread's own atoms and stay in registers.
+  __host__ __device__ static constexpr int slot_pitch(int q) { return q == QMAX ? 3 * G * RLAST : 3 * NA; }
+  __host__ __device__ static constexpr int slot_base(int q) {   // in floats, from the start of the slot area
+    int o = 0;
+    for (int i = 1; i < q; ++i) o += (i % G == 0) ? 0 : CPB * slot_pitch(i);
+    return o;
+  }
+  static constexpr int kSlotFloats = slot_base(QMAX + 1);
+  static constexpr int kSmemBytes = kPosBytes + kSlotFloats * 4 + 2 * G * CPB * 16;
+};
+
+template <int NA, int G, int CW, bool FORCE, int MINB>
+__global__ void __launch_bounds__(LJPairCfg<NA, G, CW>::kThreads, MINB)
+lj_pairs_kernel(const float *__restrict__ x, int64_t B, float inv_T, float energy_factor, float osc,
+                float *__restrict__ logp, float *__restrict__ force) {
+  using C = LJPairCfg<NA, G, CW>;
+  constexpr int S = C::S, K = C::K, T = C::T, D = 3 * NA;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *s_pos = reinterpret_cast<float *>(smem_raw);                     // [CPB][3*NA], the global layout
+  float *s_react = reinterpret_cast<float *>(smem_raw + C::kPosBytes);    // reaction slots
+  float4 *s_part = reinterpret_cast<float4 *>(s_react + C::kSlotFloats);  // [2][G][CPB]: (sum x, sum y, sum z) / energy
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = warp % G, cset = warp / G;
+  const int c = cset * 32 + lane;
+  const int64_t cfg0 = (int64_t)blockIdx.x * C::CPB;
+  const int ncfg = (int)min((int64_t)C::CPB, B - cfg0);
+  const int nflt = ncfg * D;
+  const float *__restrict__ src = x + cfg0 * D;
+
+  // ---- stage: straight float4 copy; a configuration's row pitch (3*NA floats) is odd, so lane = configuration
+  //      makes every scalar LDS / STS below bank-conflict free
+  {
+    const int nvec = nflt >> 2;
+    for (int v = tid; v < nvec; v += C::kThreads)
+      reinterpret_cast<float4 *>(s_pos)[v] = __ldg(reinterpret_cast<const float4 *>(src) + v);
+    for (int f = (nvec << 2) + tid; f < nflt; f += C::kThreads) s_pos[f] = __ldg(src + f);
+  }
+  __syncthreads();
+
+  const bool active = c < ncfg;
+  const float *__restrict__ cfg = s_pos + c * D;
+  float ax[S], ay[S], az[S];
+  f2 fx[S], fy[S], fz[S];   // packed partial sums of P = -fs*d over the pairs where the atom is on the "a" side
+  float e_pairs = 0.f;
+  if (active) {
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+      ax[r] = cfg[3 * (g * S + r) + 0]; ay[r] = cfg[3 * (g * S + r) + 1]; az[r] = cfg[3 * (g * S + r) + 2];
+      sx += ax[r]; sy += ay[r]; sz += az[r];
+      fx[r] = pk2(0.f, 0.f); fy[r] = pk2(0.f, 0.f); fz[r] = pk2(0.f, 0.f);
+    }
+    s_part[g * C::CPB + c] = make_float4(sx, sy, sz, 0.f);
+
+    const f2 eps2 = pk2(kBgflowEps, kBgflowEps);
+    f2 e6 = pk2(0.f, 0.f), en3 = pk2(0.f, 0.f);
+#pragma unroll
+    for (int t0 = 1; t0 <= T; t0 += 2) {
+      const int t1 = t0 + 1;
+      const bool has1 = t1 <= T;
+      int b0 = g * S + t0; b0 -= (b0 >= NA) ? NA : 0;
+      int b1 = g * S + (has1 ? t1 : t0); b1 -= (b1 >= NA) ? NA : 0;
+      // scalar loads straight into the halves of the packed operands (a vector load would need re-packing moves)
+      const f2 bx = pk2(lds1(cfg + 3 * b0 + 0), lds1(cfg + 3 * b1 + 0));
+      const f2 by = pk2(lds1(cfg + 3 * b0 + 1), lds1(cfg + 3 * b1 + 1));
+      const f2 bz = pk2(lds1(cfg + 3 * b0 + 2), lds1(cfg + 3 * b1 + 2));
+      f2 rx = pk2(0.f, 0.f), ry = pk2(0.f, 0.f), rz = pk2(0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        const bool v0 = (t0 - r >= 1) && (t0 - r <= K);
+        const bool v1 = has1 && (t1 - r >= 1) && (t1 - r <= K);
+        if (v0 || v1) {
+          const f2 dx = sub2(pk2(ax[r], ax[r]), bx), dy = sub2(pk2(ay[r], ay[r]), by), dz = sub2(pk2(az[r], az[r]), bz);
+          f2 s = fma2(dx, dx, eps2);
+          s = fma2(dy, dy, s);
+          s = fma2(dz, dz, s);
+          if (!v0) s = add2(s, pk2(1e30f, 0.f));
+          if (!v1) s = add2(s, pk2(0.f, 1e30f));
+          float s_lo, s_hi;
+          unpk2(s, s_lo, s_hi);
+          const f2 ninv = pk2(fast_rcp(-s_lo), fast_rcp(-s_hi));   // -1/s
+          const f2 inv2 = mul2(ninv, ninv);                         //  1/s^2
+          const f2 ni3 = mul2(inv2, ninv);                          // -1/s^3
+          e6 = fma2(ni3, ni3, e6);                                  // sum r^-12
+          en3 = add2(en3, ni3);                                     // -sum r^-6
+          if (FORCE) {
+            const f2 w = mul2(inv2, inv2);                          //  1/s^4
+            const f2 nfs = fma2(w, ni3, w);                         // -(s^-6 - s^-3)/s
+            fx[r] = fma2(nfs, dx, fx[r]); fy[r] = fma2(nfs, dy, fy[r]); fz[r] = fma2(nfs, dz, fz[r]);
+            rx = fma2(nfs, dx, rx); ry = fma2(nfs, dy, ry); rz = fma2(nfs, dz, rz);
+          }
+        }
+      }
+      if (FORCE) {
+        // reaction on the streamed atoms: +fs*d(b) = the same product P, but the owner's accumulator carries -P
+        float xl, xh, yl, yh, zl, zh;
+        unpk2(rx, xl, xh); unpk2(ry, yl, yh); unpk2(rz, zl, zh);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int t = half ? t1 : t0;
+          if (half && !has1) continue;
+          const int q = t / S, r_t = t % S;
+          const float vx = half ? xh : xl, vy = half ? yh : yl, vz = half ? zh : zl;
+          if (q % G == 0) {                      // one of this thread's own atoms: registers
+            float lo, hi;
+            unpk2(fx[r_t], lo, hi); fx[r_t] = pk2(lo - vx, hi);
+            unpk2(fy[r_t], lo, hi); fy[r_t] = pk2(lo - vy, hi);
+            unpk2(fz[r_t], lo, hi); fz[r_t] = pk2(lo - vz, hi);
+          } else {
+            int gt = g + q % G; gt -= (gt >= G) ? G : 0;
+            float *d = s_react + C::slot_base(q) + c * C::slot_pitch(q) +
+                       (q == C::QMAX ? 3 * (gt * C::RLAST + r_t) : 3 * (gt * S + r_t));
+            d[0] = vx; d[1] = vy; d[2] = vz;
+          }
+        }
+      }
+    }
+    float a_lo, a_hi, b_lo, b_hi;
+    unpk2(e6, a_lo, a_hi);
+    unpk2(en3, b_lo, b_hi);
+    e_pairs = (a_lo + a_hi) + 2.0f * (b_lo + b_hi);  // sum over this thread's unordered pairs of r^-12 - 2 r^-6
+  }
+  __syncthreads();
+
+  // ---- centre of mass, harmonic term, reaction gather
+  float fo[FORCE ? 3 * S : 1];
+  if (active) {
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg) {
+      const float4 q = s_part[gg * C::CPB + c];
+      cx += q.x; cy += q.y; cz += q.z;
+    }
+    cx *= (1.0f / NA); cy *= (1.0f / NA); cz *= (1.0f / NA);
+    const float k24 = 24.0f * energy_factor * inv_T, ko = osc * inv_T;
+    float e_osc = 0.f;
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+      const float ux = ax[r] - cx, uy = ay[r] - cy, uz = az[r] - cz;
+      e_osc = fmaf(ux, ux, fmaf(uy, uy, fmaf(uz, uz, e_osc)));
+      if (FORCE) {
+        float lo, hi, px, py, pz;
+        unpk2(fx[r], lo, hi); px = -(lo + hi);
+        unpk2(fy[r], lo, hi); py = -(lo + hi);
+        unpk2(fz[r], lo, hi); pz = -(lo + hi);
+#pragma unroll
+        for (int q = 1; q <= C::QMAX; ++q) {
+          if (q % G != 0 && q * S + r <= T) {    // thread g - q streamed this atom at step t = q*S + r
+            const float *sp = s_react + C::slot_base(q) + c * C::slot_pitch(q) +
+                              (q == C::QMAX ? 3 * (g * C::RLAST + r) : 3 * (g * S + r));
+            px += sp[0]; py += sp[1]; pz += sp[2];
+          }
+        }
+        fo[3 * r + 0] = fmaf(k24, px, -ko * ux);
+        fo[3 * r + 1] = fmaf(k24, py, -ko * uy);
+        fo[3 * r + 2] = fmaf(k24, pz, -ko * uz);
+      }
+    }
+    // reference energy sums ORDERED pairs (= 2 x unordered), lennardjones_energy.py:121-140
+    s_part[(G + g) * C::CPB + c] = make_float4(0.f, 0.f, 0.f, energy_factor * 2.0f * e_pairs + osc * 0.5f * e_osc);
+  }
+  __syncthreads();
+  if (g == 0 && active) {
+    float v = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg) v += s_part[(G + gg) * C::CPB + c].w;
+    logp[cfg0 + c] = -v * inv_T;
+  }
+  if (FORCE) {
+    float *s_out = s_pos;  // coordinates are dead (registers hold them): reuse as the coalescing stage
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        float *o = s_out + c * D + 3 * (g * S + r);
+        o[0] = fo[3 * r + 0]; o[1] = fo[3 * r + 1]; o[2] = fo[3 * r + 2];
+      }
+    }
+    __syncthreads();
+    float *__restrict__ dst = force + cfg0 * D;
+    const int nvec = nflt >> 2;
+    for (int v = tid; v < nvec; v += C::kThreads)
+      reinterpret_cast<float4 *>(dst)[v] = reinterpret_cast<const float4 *>(s_out)[v];
+    for (int f = (nvec << 2) + tid; f < nflt; f += C::kThreads) dst[f] = s_out[f];
+  }
+}
+
+template <int NA, int G, int CW, int MINB>
+static int launch_lj_pairs(const float *x, int64_t B, float T, float ef, float osc, float *logp, float *force,
+                           cudaStream_t st) {
+  using C = LJPairCfg<NA, G, CW>;
+  const int64_t blocks = (B + C::CPB - 1) / C::CPB;
+  PITA_REQUIRE(blocks < (1ll << 31), PITA_EINVAL, "lj: batch too large");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(lj_pairs_kernel<NA, G, CW, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaFuncSetAttribute(lj_pairs_kernel<NA, G, CW, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    attr_set = true;
+  }
+  if (force != nullptr)
+    lj_pairs_kernel<NA, G, CW, true, MINB><<<(unsigned)blocks, C::kThreads, C::kSmemBytes, st>>>(x, B, 1.0f / T, ef, osc, logp, force);
+  else
+    lj_pairs_kernel<NA, G, CW, false, MINB><<<(unsigned)blocks, C::kThreads, C::kSmemBytes, st>>>(x, B, 1.0f / T, ef, osc, logp, force);
+  PITA_CHECK_LAUNCH("lj_pairs_kernel");
+  return PITA_OK;
+}
+
 template <int NA, int CPB>
 static int launch_lj(const float *x, int64_t B, float T, float ef, float osc, float *logp, float *force,
                      cudaStream_t st) {
@@ -146,9 +412,15 @@ extern "C" int pita_lj_energy_force(const float *x, int64_t B, int n, float temp
   PITA_REQUIRE(temperature > 0.f, PITA_EINVAL, "lj: temperature must be positive");
   if (B == 0) return PITA_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // PITA_LJ_KERNEL=ordered selects the scalar ordered-pair kernel (kept for A/B measurements; same results to rounding)
+  static const bool ordered = [] { const char *e = getenv("PITA_LJ_KERNEL"); return e && e[0] == 'o'; }();
   switch (n) {
-    case 13: return launch_lj<13, 32>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
-    case 55: return launch_lj<55, 8>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+    case 13:
+      if (ordered) return launch_lj<13, 32>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+      return launch_lj_pairs<13, 1, 4, 3>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+    case 55:
+      if (ordered) return launch_lj<55, 8>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+      return launch_lj_pairs<55, 5, 1, 2>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
     default:
       set_error("lj: n_particles=%d unsupported (reference raises NotImplementedError for n not in {13,55}, "
                 "lennardjones_energy.py:177-178)", n);
