@@ -236,10 +236,11 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved_tf = alg_flops / (k_ms * 1e-3) / 1e12
-    roofline = {"kernel": "egnn_score_div_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+    roofline = {"kernel": "egnn_score_div_rows_kernel (%s)" % ops.default_div_mode(), "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": None, "kernel_ms": k_ms,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
-                "note": "algorithmic FLOPs = (3n+1) dense EGNN forwards per particle (SURVEY 8d); this round's kernel is fp32 SIMT"}
+                "note": "algorithmic FLOPs = (3n+1) dense EGNN forwards per particle (SURVEY 8d); the kernel executes ~21 (n=13) / ~76 (n=55) "
+                        "forward-equivalents (structured tangents) as tcgen05 kind::tf32 MMAs (x3 in 3xtf32 mode) against the bf16 peak"}
 
     # ---- end to end through the public step with HOST buffers: H2D of (x, a), one FK step, D2H of (x', a')
     hx = torch.empty(Nl, D, pin_memory=True).copy_(x.cpu())

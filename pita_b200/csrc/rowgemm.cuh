@@ -112,15 +112,20 @@ struct Team {
     const uint32_t wa = w_addr + (uint32_t)wslot * (uint32_t)Bytes<SPLIT>::kW;
     const uint64_t dA = umma::make_desc_sw128_kmajor(a_addr);
     const uint64_t dB = umma::make_desc_sw128_kmajor(wa);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) umma::mma_tf32_ss(d, dA + 2 * k, dB + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
     if (SPLIT) {
+      // 3xTF32: the two correction products first, so that their partial sums are rounded (the tensor core truncates
+      // the fp32 accumulator) at their own small magnitude and only the four hi*hi steps round at full magnitude.
       const uint64_t dAl = umma::make_desc_sw128_kmajor(a_addr + 16384u);
       const uint64_t dBl = umma::make_desc_sw128_kmajor(wa + 4096u);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma::mma_tf32_ss(d, dAl + 2 * k, dB + 2 * k, idesc, 1u);
+      for (int k = 0; k < 4; ++k) umma::mma_tf32_ss(d, dAl + 2 * k, dB + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma::mma_tf32_ss(d, dA + 2 * k, dBl + 2 * k, idesc, 1u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma::mma_tf32_ss(d, dA + 2 * k, dB + 2 * k, idesc, 1u);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma::mma_tf32_ss(d, dA + 2 * k, dB + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
     }
   }
 
