@@ -190,7 +190,7 @@ struct LJPairCfg {
     return o;
   }
   static constexpr int kSlotFloats = slot_base(QMAX + 1);
-  static constexpr int kSmemBytes = kPosBytes + kSlotFloats * 4 + 2 * G * CPB * 16;
+  static constexpr int kSmemBytes = kPosBytes + kSlotFloats * 4 + G * CPB * 16;   // one [G][CPB] float4 area, used twice
 };
 
 template <int NA, int G, int CW, bool FORCE, int MINB>
@@ -202,7 +202,7 @@ lj_pairs_kernel(const float *__restrict__ x, int64_t B, float inv_T, float energ
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *s_pos = reinterpret_cast<float *>(smem_raw);                     // [CPB][3*NA], the global layout
   float *s_react = reinterpret_cast<float *>(smem_raw + C::kPosBytes);    // reaction slots
-  float4 *s_part = reinterpret_cast<float4 *>(s_react + C::kSlotFloats);  // [2][G][CPB]: (sum x, sum y, sum z) / energy
+  float4 *s_part = reinterpret_cast<float4 *>(s_react + C::kSlotFloats);  // [G][CPB]: (sum x, sum y, sum z), later .w = energy
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = warp % G, cset = warp / G;
@@ -309,6 +309,7 @@ lj_pairs_kernel(const float *__restrict__ x, int64_t B, float inv_T, float energ
 
   // ---- centre of mass, harmonic term, reaction gather
   float fo[FORCE ? 3 * S : 1];
+  float e_total = 0.f;
   if (active) {
     float cx = 0.f, cy = 0.f, cz = 0.f;
 #pragma unroll
@@ -342,13 +343,15 @@ lj_pairs_kernel(const float *__restrict__ x, int64_t B, float inv_T, float energ
       }
     }
     // reference energy sums ORDERED pairs (= 2 x unordered), lennardjones_energy.py:121-140
-    s_part[(G + g) * C::CPB + c] = make_float4(0.f, 0.f, 0.f, energy_factor * 2.0f * e_pairs + osc * 0.5f * e_osc);
+    e_total = energy_factor * 2.0f * e_pairs + osc * 0.5f * e_osc;
   }
+  __syncthreads();   // every group has read the centre-of-mass partials: the area is reused for the energy partials
+  if (active) s_part[g * C::CPB + c].w = e_total;
   __syncthreads();
   if (g == 0 && active) {
     float v = 0.f;
 #pragma unroll
-    for (int gg = 0; gg < G; ++gg) v += s_part[(G + gg) * C::CPB + c].w;
+    for (int gg = 0; gg < G; ++gg) v += s_part[gg * C::CPB + c].w;
     logp[cfg0 + c] = -v * inv_T;
   }
   if (FORCE) {
@@ -414,12 +417,15 @@ extern "C" int pita_lj_energy_force(const float *x, int64_t B, int n, float temp
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // PITA_LJ_KERNEL=ordered selects the scalar ordered-pair kernel (kept for A/B measurements; same results to rounding)
   static const bool ordered = [] { const char *e = getenv("PITA_LJ_KERNEL"); return e && e[0] == 'o'; }();
+  // PITA_LJ_MINB=3: LJ-55 variant compiled for three resident CTAs per SM (<= 136 registers) instead of two
+  static const bool minb3 = [] { const char *e = getenv("PITA_LJ_MINB"); return e && e[0] == '3'; }();
   switch (n) {
     case 13:
       if (ordered) return launch_lj<13, 32>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
       return launch_lj_pairs<13, 1, 4, 3>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
     case 55:
       if (ordered) return launch_lj<55, 8>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+      if (minb3) return launch_lj_pairs<55, 5, 1, 3>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
       return launch_lj_pairs<55, 5, 1, 2>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
     default:
       set_error("lj: n_particles=%d unsupported (reference raises NotImplementedError for n not in {13,55}, "
