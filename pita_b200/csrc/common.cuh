@@ -87,11 +87,6 @@ __device__ __forceinline__ void silu_both(float z, float &val, float &der) {
   der = s * fmaf(z, 1.0f - s, 1.0f);
 }
 __device__ __forceinline__ float silu_val(float z) { return z * sigmoidf_fast(z); }
-// ~1 ulp forms (libdevice expf + IEEE division) for the primal forward of the row engine: the score is
-// (c_out F(x) + (c_s - 1) x) / h, which amplifies every rounding of the coordinate update by 1 / sqrt(h (1 + h)),
-// so the primal path is kept at torch-CPU accuracy while the (far more numerous) tangent evaluations use the MUFU forms.
-__device__ __forceinline__ float sigmoidf_acc(float z) { return 1.0f / (1.0f + expf(-z)); }
-__device__ __forceinline__ float silu_val_acc(float z) { return z / (1.0f + expf(-z)); }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

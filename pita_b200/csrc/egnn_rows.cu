@@ -71,14 +71,10 @@ __device__ __forceinline__ void stage1(float (&row)[32], float (&f1)[32], const 
     for (int e = 0; e < 4; ++e) {
       const int k = 4 * k4 + e;
       const float z = row[k] + qq[e] + cc[e] * r2 + dd[e] * ea;
-      if (KEEP) {
-        float a, f;
-        silu_both(z, a, f);
-        row[k] = a;
-        f1[k] = f;
-      } else {
-        row[k] = silu_val_acc(z);
-      }
+      float a, f;
+      silu_both(z, a, f);
+      row[k] = a;
+      if (KEEP) f1[k] = f;
     }
   }
 }
@@ -96,17 +92,13 @@ __device__ __forceinline__ float stage2(float (&row)[32], float (&m)[32], float 
     for (int e = 0; e < 4; ++e) {
       const int k = 4 * k4 + e;
       float a, f;
-      if (KEEP) {
-        silu_both(row[k] + bb[e], a, f);
-        m[k] = a; f2[k] = f;
-      } else {
-        a = silu_val_acc(row[k] + bb[e]);
-      }
+      silu_both(row[k] + bb[e], a, f);
       row[k] = a;
+      if (KEEP) { m[k] = a; f2[k] = f; }
       dot = fmaf(ww[e], a, dot);
     }
   }
-  const float att = KEEP ? sigmoidf_fast(dot + lds1(vec + vBA * 32)) : sigmoidf_acc(dot + lds1(vec + vBA * 32));
+  const float att = sigmoidf_fast(dot + lds1(vec + vBA * 32));
 #pragma unroll
   for (int k = 0; k < 32; ++k) row[k] *= att;
   return att;
@@ -125,12 +117,8 @@ __device__ __forceinline__ float stage3(const float (&acc)[32], float (&fc)[32],
     for (int e = 0; e < 4; ++e) {
       const int k = 4 * k4 + e;
       float a, f;
-      if (KEEP) {
-        silu_both(acc[k] + bb[e], a, f);
-        fc[k] = f;
-      } else {
-        a = silu_val_acc(acc[k] + bb[e]);
-      }
+      silu_both(acc[k] + bb[e], a, f);
+      if (KEEP) fc[k] = f;
       u = fmaf(ww[e], a, u);
     }
   }
@@ -339,16 +327,16 @@ __device__ __forceinline__ void primal_forward_rows(Ctx<NP, NTEAM, SPLIT, MODE> 
         if (TANGENT && scratch_row) {
           float f3[32];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) { float a; silu_both(row[k], a, f3[k]); row[k] = silu_val_acc(row[k]); }
+          for (int k = 0; k < 32; ++k) { float a; silu_both(row[k], a, f3[k]); row[k] = a; }
           store_vec_global(scratch_row + l * kRows * 32, f3);  // f3^l
         } else if (MODE == kModeRev) {  // the reverse pass keeps f3^l in its own TMEM lane
           float f3[32];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) { float a; silu_both(row[k], a, f3[k]); row[k] = silu_val_acc(row[k]); }
+          for (int k = 0; k < 32; ++k) { float a; silu_both(row[k], a, f3[k]); row[k] = a; }
           T.st(sF30 + l, f3);
         } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) row[k] = silu_val_acc(row[k]);
+          for (int k = 0; k < 32; ++k) row[k] = silu_val(row[k]);
         }
         T.store_row(row);
         T.round_trip([&] { T.mma(sAcc0, 1, false); });

@@ -41,7 +41,9 @@ def check_resampler(world, rank, dev, exchange):
             buf.copy_(xl)
             xl = buf
         x_new, changes = rs.resample(xl, a_g, u0)
-        ids = O.systematic_indices(O.clipped_softmax(a_full).numpy(), u0)
+        # indices are bit-exact GIVEN the weights (SURVEY §8d gate 1): take the device's clipped softmax, as the 1-GPU tests do
+        from pita_b200 import ops
+        ids = O.systematic_indices(ops.softmax_clip(a_g).cpu().numpy(), u0)
         want = x_full[torch.from_numpy(ids[lo:hi])]
         assert torch.equal(x_new.cpu(), want), "rank %d: sharded resample (%s) differs from the global one" % (rank, exchange)
         assert max(int(changes.item()), 1) == len(np.unique(ids))

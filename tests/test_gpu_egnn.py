@@ -109,7 +109,13 @@ def test_kernels_vs_fp64_oracle_random(n, B, gain, mode):
     # bar here is 5e-4; the golden-fixture tests above hold dU/dt to 1e-4.
     assert_close(dh.double().cpu() * sched.dh_dt(t), gt, "dE/dt", rtol=5e-4)
     s, d = ops.egnn_score_div(wS, 32, 3, n, ht.float().cuda(), x.float().cuda(), beta, mode=mode)
-    assert_close(s, s_ref, "score")
+    # Score bar: 1e-4 norm-wise everywhere (measured <= 2.6e-6) and 1e-4 element-wise, except on the tensor-core (3xTF32) path
+    # for the LJ-55 / strong-gain case, whose first particle (h = 0.0087) evaluates (c_s x + c_out F - x) / h with a
+    # 1 / sqrt(h (1 + h)) = 10.7x amplification of every rounding in F: measured 1.0e-4 .. 1.3e-4 there (fp32 SIMT kernel
+    # 0.9e-4, the reference's own fp32 arithmetic 2e-5; profiles/r1e_err_by_mode.jsonl).  north_star allows a stated looser
+    # bound on a TF32 MLP path: 2.5e-4 element-wise for exactly this case.
+    loose = mode != "fp32" and n == 55 and gain > 0.1
+    assert_close(s, s_ref, "score", rtol=2.5e-4 if loose else 1e-4, norm_rtol=1e-4)
     assert_close(d, div_ref, "div (%s)" % mode, rtol=DIV_TOL[mode])
 
 
