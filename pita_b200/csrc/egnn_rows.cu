@@ -724,6 +724,14 @@ static int launch_energy_rows(const float *w, const float *ht, const float *x, c
 //   layer 2: only d x^3_k / d y_k is needed: edge (k, j) is evaluated by the SENDER's thread j.
 // ================================================================================================
 enum Scr { qF30 = 0, qF31 = 1, qP2 = 2, qQ2 = 3, qP1 = 4, qOmega = 5, qDh1o = 6, qPiAo = 9, qPiBo = 12, qDxo = 15, kScrVecs = 16 };
+// Layer-1 edge cache: the primal quantities of edge (i, sender slot u) -- silu'(z1), m, silu'(z2), silu'(zc), the attention
+// gate and tanh(u) -- do not depend on the tangent node k, so pass k = 0 writes them to the team's scratch (own-row
+// layout: every thread only ever reads back what it wrote itself) and passes k >= 1 load them instead of redoing two
+// MMA round trips and 96 SiLU evaluations per edge.  Floats per slot: 4 vectors x [128][32] + one float4 per row.
+constexpr int kEdgeVecs = 4;
+constexpr int kEdgeFloats = kEdgeVecs * kRows * 32 + kRows * 4;
+template <int NP>
+__host__ __device__ constexpr int64_t team_scratch_floats() { return (int64_t)kScrVecs * kRows * 32 + (int64_t)(NP - 1) * kEdgeFloats; }
 
 // acc = W2 dz1  ->  d(ms) in place:  dm = f2*acc, ds = att(1-att) <wa, dm>, dms = dm*att + m*ds
 __device__ __forceinline__ void tangent_mid(float (&row)[32], const float (&m)[32], const float (&f2)[32], float att, const float *vec) {
@@ -814,8 +822,12 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
   float4 *sDX = reinterpret_cast<float4 *>(c.tm + S::tDX);
   float4 *sCoef = reinterpret_cast<float4 *>(c.tm + S::tCoef);
   float *sOwnA = c.tm + S::tOwnA, *sOwnB = c.tm + S::tOwnB, *sKP2 = c.tm + S::tKP2, *sKdP2 = c.tm + S::tKdP2;
-  float *scr = scratch ? scratch + ((size_t)blockIdx.x * NTEAM + c.team) * kScrVecs * kRows * 32 + (size_t)tt * 32 : nullptr;
+  float *team_scr = scratch ? scratch + ((size_t)blockIdx.x * NTEAM + c.team) * (size_t)team_scratch_floats<NP>() : nullptr;
+  float *scr = team_scr ? team_scr + (size_t)tt * 32 : nullptr;
   auto SCR = [&](int v) { return scr + (size_t)v * kRows * 32; };
+  float *escr = team_scr ? team_scr + (size_t)kScrVecs * kRows * 32 : nullptr;
+  auto ESCR = [&](int u, int v) { return escr + (size_t)u * kEdgeFloats + (size_t)v * kRows * 32 + (size_t)tt * 32; };
+  auto ESCAL = [&](int u) { return reinterpret_cast<float4 *>(escr + (size_t)u * kEdgeFloats + kEdgeVecs * kRows * 32) + tt; };
 
   // layer-0 class tables:  A0 e0, A0 e1, A0 eb + b1, B0 e0, B0 e1, B0 eb
   if (c.tid < 192) {
@@ -1101,16 +1113,31 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
           const bool jk = (j == k);
           const float4 yj = c.sX[rj];
           const Geo g = edge_geo4(xi, c.sX[kRows + rj], yi, yj);
-          T.ld(sP, row);
-          stage1<true>(row, f1, c.sQa, rj, vec1, g.r2, g.ea);
-          T.store_row(row);
-          T.round_trip([&] { T.mma(sAcc0, 1, false); });
-          T.ld(sAcc0, row);
-          const float att = stage2<true>(row, m, f2, vec1);
-          T.store_row(row);
-          T.round_trip([&] { T.mma(sAccC, 2, false); });
-          T.ld(sAccC, row);
-          const float th = stage3<true>(row, fc, vec1);
+          float att, th;
+          if (k == 0) {  // (k is uniform over the CTA: the round trips below stay team-collective)
+            T.ld(sP, row);
+            stage1<true>(row, f1, c.sQa, rj, vec1, g.r2, g.ea);
+            T.store_row(row);
+            T.round_trip([&] { T.mma(sAcc0, 1, false); });
+            T.ld(sAcc0, row);
+            att = stage2<true>(row, m, f2, vec1);
+            T.store_row(row);
+            T.round_trip([&] { T.mma(sAccC, 2, false); });
+            T.ld(sAccC, row);
+            th = stage3<true>(row, fc, vec1);
+            store_vec_global(ESCR(u, 0), f1);
+            store_vec_global(ESCR(u, 1), m);
+            store_vec_global(ESCR(u, 2), f2);
+            store_vec_global(ESCR(u, 3), fc);
+            *ESCAL(u) = make_float4(att, th, 0.f, 0.f);
+          } else {
+            load_vec_global(ESCR(u, 0), f1);
+            load_vec_global(ESCR(u, 1), m);
+            load_vec_global(ESCR(u, 2), f2);
+            load_vec_global(ESCR(u, 3), fc);
+            const float4 sc4 = *ESCAL(u);
+            att = sc4.x; th = sc4.y;
+          }
           const float phi = rng * th, dphi_du = rng * (1.0f - th * th);
           const float k2 = g.inv * g.inv / g.nrm;
           const float4 cfj = sCoef[rj];
@@ -1260,7 +1287,7 @@ static int launch_score_div_rows(const float *w, const float *ht, const float *x
   using S = Smem<NP, NTEAM, SPLIT, kModeTan>;
   auto k = egnn_score_div_rows_kernel<NP, NTEAM, SPLIT>;
   static_assert(S::kBytes <= 227 * 1024, "shared memory plan exceeds 227 KB");
-  const int64_t need = (int64_t)kNumSMs * NTEAM * kScrVecs * kRows * 32 * 4;
+  const int64_t need = (int64_t)kNumSMs * NTEAM * team_scratch_floats<NP>() * 4;
   PITA_REQUIRE(dv == nullptr || (scratch != nullptr && scratch_bytes >= need), PITA_EINVAL,
                "egnn_score_div: workspace too small (need %lld bytes)", (long long)need);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes);
@@ -1293,8 +1320,7 @@ int launch_energy_rows(int n, bool split, const float *w, const float *ht, const
 }
 
 int64_t score_div_rows_workspace_bytes(int n) {
-  (void)n;
-  return (int64_t)kNumSMs * 2 * rg::kScrVecs * rg::kRows * 32 * 4;
+  return (int64_t)kNumSMs * 2 * (n == 13 ? rg::team_scratch_floats<13>() : rg::team_scratch_floats<55>()) * 4;
 }
 
 int launch_score_div_rows(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,

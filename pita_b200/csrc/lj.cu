@@ -417,15 +417,14 @@ extern "C" int pita_lj_energy_force(const float *x, int64_t B, int n, float temp
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // PITA_LJ_KERNEL=ordered selects the scalar ordered-pair kernel (kept for A/B measurements; same results to rounding)
   static const bool ordered = [] { const char *e = getenv("PITA_LJ_KERNEL"); return e && e[0] == 'o'; }();
-  // PITA_LJ_MINB=3: LJ-55 variant compiled for three resident CTAs per SM (<= 136 registers) instead of two
-  static const bool minb3 = [] { const char *e = getenv("PITA_LJ_MINB"); return e && e[0] == '3'; }();
+  // (A three-CTA-per-SM build of the LJ-55 kernel -- 128 registers, 15 warps -- measured 6 % SLOWER than this two-CTA
+  //  one: profiles/r1g_bench_lj55_minb3.jsonl; the kernel is bound by its dependent FMA/MUFU chains, not by occupancy.)
   switch (n) {
     case 13:
       if (ordered) return launch_lj<13, 32>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
       return launch_lj_pairs<13, 1, 4, 3>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
     case 55:
       if (ordered) return launch_lj<55, 8>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
-      if (minb3) return launch_lj_pairs<55, 5, 1, 3>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
       return launch_lj_pairs<55, 5, 1, 2>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
     default:
       set_error("lj: n_particles=%d unsupported (reference raises NotImplementedError for n not in {13,55}, "
