@@ -826,7 +826,7 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
   float *scr = team_scr ? team_scr + (size_t)tt * 32 : nullptr;
   auto SCR = [&](int v) { return scr + (size_t)v * kRows * 32; };
   float *escr = team_scr ? team_scr + (size_t)kScrVecs * kRows * 32 : nullptr;
-  auto ESCR = [&](int u, int v) { return escr + (size_t)u * kEdgeFloats + (size_t)v * kRows * 32 + (size_t)tt * 32; };
+  auto ESCR = [&](int u, int v) { return escr + (size_t)u * kEdgeFloats + (size_t)v * kRows * 32; };  // coalesced block
   auto ESCAL = [&](int u) { return reinterpret_cast<float4 *>(escr + (size_t)u * kEdgeFloats + kEdgeVecs * kRows * 32) + tt; };
 
   // layer-0 class tables:  A0 e0, A0 e1, A0 eb + b1, B0 e0, B0 e1, B0 eb
@@ -1001,6 +1001,46 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
       }
     }
 
+    // =========================== layer-1 edge cache (see kEdgeFloats): f1, m, f2, v = Wc1^T (wc2 * fc), att, tanh(u)
+    {
+      WeightSrc sL1;
+      sL1.p[0] = W1 + pk::W2_b; sL1.p[1] = W1 + pk::Wc1_b; sL1.p[2] = W1 + pk::Wc1_f;
+      sL1.count = 3;
+      load_weights(c, sL1);
+      if (team_active) {
+        const float4 xi = c.sX[kRows + tt];
+#pragma unroll 1
+        for (int u = 0; u < NP - 1; ++u) {
+          const int rj = pp * NP + c.sender(u);
+          const Geo g = edge_geo4(xi, c.sX[kRows + rj], yi, c.sX[rj]);
+          T.ld(sP, row);
+          stage1<true>(row, f1, c.sQa, rj, vec1, g.r2, g.ea);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAcc0, 0, false); });
+          T.ld(sAcc0, row);
+          const float att = stage2<true>(row, m, f2, vec1);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAccC, 1, false); });
+          T.ld(sAccC, row);
+          const float th = stage3<true>(row, fc, vec1);
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 w = lds4(vec1 + vWC2 * 32 + 4 * k4);
+            row[4 * k4] = w.x * fc[4 * k4]; row[4 * k4 + 1] = w.y * fc[4 * k4 + 1];
+            row[4 * k4 + 2] = w.z * fc[4 * k4 + 2]; row[4 * k4 + 3] = w.w * fc[4 * k4 + 3];
+          }
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sAcc0, 2, false); });
+          T.ld(sAcc0, row);  // v_ij
+          store_vec_global_co(ESCR(u, 0), tt, f1);
+          store_vec_global_co(ESCR(u, 1), tt, m);
+          store_vec_global_co(ESCR(u, 2), tt, f2);
+          store_vec_global_co(ESCR(u, 3), tt, row);
+          __stcg(ESCAL(u), make_float4(att, th, 0.f, 0.f));
+        }
+      }
+    }
+
     // =========================== passes over the tangent node k
     float trace = 0.f;
 #pragma unroll 1
@@ -1113,35 +1153,16 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
           const bool jk = (j == k);
           const float4 yj = c.sX[rj];
           const Geo g = edge_geo4(xi, c.sX[kRows + rj], yi, yj);
-          float att, th;
-          if (k == 0) {  // (k is uniform over the CTA: the round trips below stay team-collective)
-            T.ld(sP, row);
-            stage1<true>(row, f1, c.sQa, rj, vec1, g.r2, g.ea);
-            T.store_row(row);
-            T.round_trip([&] { T.mma(sAcc0, 1, false); });
-            T.ld(sAcc0, row);
-            att = stage2<true>(row, m, f2, vec1);
-            T.store_row(row);
-            T.round_trip([&] { T.mma(sAccC, 2, false); });
-            T.ld(sAccC, row);
-            th = stage3<true>(row, fc, vec1);
-            store_vec_global(ESCR(u, 0), f1);
-            store_vec_global(ESCR(u, 1), m);
-            store_vec_global(ESCR(u, 2), f2);
-            store_vec_global(ESCR(u, 3), fc);
-            *ESCAL(u) = make_float4(att, th, 0.f, 0.f);
-          } else {
-            load_vec_global(ESCR(u, 0), f1);
-            load_vec_global(ESCR(u, 1), m);
-            load_vec_global(ESCR(u, 2), f2);
-            load_vec_global(ESCR(u, 3), fc);
-            const float4 sc4 = *ESCAL(u);
-            att = sc4.x; th = sc4.y;
-          }
+          // primal quantities of this edge from the layer-1 edge cache (filled once per tile, before the passes)
+          load_vec_global_co(ESCR(u, 0), tt, f1);
+          load_vec_global_co(ESCR(u, 1), tt, m);
+          load_vec_global_co(ESCR(u, 2), tt, f2);
+          load_vec_global_co(ESCR(u, 3), tt, fc);  // fc <- v_ij = Wc1^T (wc2 * silu'(zc))
+          const float4 sc4 = __ldcg(ESCAL(u));
+          const float att = sc4.x, th = sc4.y;
           const float phi = rng * th, dphi_du = rng * (1.0f - th * th);
           const float k2 = g.inv * g.inv / g.nrm;
           const float4 cfj = sCoef[rj];
-          const float dd3[3] = {g.d0, g.d1, g.d2};
           const float e03[3] = {yi.x - yj.x, yi.y - yj.y, yi.z - yj.z};
           const float sgn = (is_k ? 1.0f : 0.0f) - (jk ? 1.0f : 0.0f);
           const bool accz = u > 0;
@@ -1169,20 +1190,37 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
             T.store_row(row);
             T.round_trip([&] { T.mma(sAcc0, 1, false); });
             T.ld(sAcc0, row);
-            tangent_mid(row, m, f2, att, vec1);
-            T.store_row(row);
-            T.round_trip([&] { T.mma(sAccC, 2, false); T.mma(sT0 + a, 3, accz); });
-            T.ld(sAccC, row);
-            const float dphi = dphi_du * tangent_du(row, fc, vec1);
+            tangent_mid(row, m, f2, att, vec1);  // row = d(m*_ij)
+            // du = <wc2 * silu'(zc), Wc1 dms> = <v_ij, dms>: a dot product with the cached vector, no MMA
+            float du = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) du = fmaf(fc[kk], row[kk], du);
+            const float dphi = dphi_du * du;
+            // d agg_i[a] += dms: summed in fp32 (round-to-nearest) in the row's own TMEM lane; W3a is applied once per
+            // direction after the slots (linearity) instead of one accumulating MMA per edge
+            {
+              float tmp[32];
+              if (accz) {
+                T.ld(sT0 + a, tmp);
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) tmp[kk] += row[kk];
+                T.st(sT0 + a, tmp);
+              } else {
+                T.st(sT0 + a, row);
+              }
+            }
             const float cg = dotD * k2;
             dx2[a][0] += (D0 * g.inv - g.d0 * cg) * phi + g.d0 * g.inv * dphi;
             dx2[a][1] += (D1 * g.inv - g.d1 * cg) * phi + g.d1 * g.inv * dphi;
             dx2[a][2] += (D2 * g.inv - g.d2 * cg) * phi + g.d2 * g.inv * dphi;
           }
         }
-        // dz3[a] += W3h1 dh^1[a]   (W3h1 sits in slot 4 of this set)
+        // dz3[a] = W3a1 dagg[a] + W3h1 dh^1[a]   (W3a1 / W3h1 sit in slots 3 / 4 of this set)
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
+          T.ld(sT0 + a, row);
+          T.store_row(row);
+          T.round_trip([&] { T.mma(sT0 + a, 3, false); });
           if (is_k) {
             load_vec_global(SCR(qDh1o + a), row);
           } else {

@@ -157,6 +157,63 @@ struct Team {
     umma::fence_after_thread_sync();
   }
 
+  // ---- TS form: the A operand row goes into the thread's own TMEM lane (two 32-column slots: hi, lo) instead of the
+  // shared-memory tile.  No STS, no generic->async proxy fence; measured 541 vs 990 cycles per 3xTF32 round trip
+  // (profiles/ubench/roundtrip.cu, bit-identical results).  The slots must not be a live accumulator.
+  __device__ __forceinline__ void store_row_tmem(int slot_hi, int slot_lo, const float (&v)[32]) const {
+    if (SPLIT) {
+      float h[32], l[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) umma::split_tf32(v[k], h[k], l[k]);
+      umma::tmem_st_32x32(tmem + 32u * slot_hi, h);
+      umma::tmem_st_32x32(tmem + 32u * slot_lo, l);
+    } else {
+      umma::tmem_st_32x32(tmem + 32u * slot_hi, v);
+    }
+  }
+  __device__ __forceinline__ void mma_ts(int dslot, int aslot_hi, int aslot_lo, int wslot, bool accumulate) const {
+    constexpr uint32_t idesc = umma::make_idesc_tf32(128, 32);
+    const uint32_t d = tmem_col + 32u * dslot, ah = tmem_col + 32u * aslot_hi, al = tmem_col + 32u * aslot_lo;
+    const uint32_t wa = w_addr + (uint32_t)wslot * (uint32_t)Bytes<SPLIT>::kW;
+    const uint64_t dB = umma::make_desc_sw128_kmajor(wa);
+    if (SPLIT) {
+      const uint64_t dBl = umma::make_desc_sw128_kmajor(wa + 4096u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma::mma_tf32_ts(d, al + 8u * k, dB + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma::mma_tf32_ts(d, ah + 8u * k, dBl + 2 * k, idesc, 1u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma::mma_tf32_ts(d, ah + 8u * k, dB + 2 * k, idesc, 1u);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma::mma_tf32_ts(d, ah + 8u * k, dB + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+    }
+  }
+  template <class F>
+  __device__ __forceinline__ void round_trip_ts(F issue) {
+    umma::fence_before_thread_sync();
+    sync();
+    if (issuer) {
+      if (elect_one()) {
+        umma::fence_after_thread_sync();
+        issue();
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_addr) : "memory");
+      }
+      __syncwarp();
+    }
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "RTS_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra RTS_DONE;\n\t"
+        "bra RTS_WAIT;\n\t"
+        "RTS_DONE:\n\t}\n" ::"r"(mbar_addr),
+        "r"(phase)
+        : "memory");
+    phase ^= 1u;
+    umma::fence_after_thread_sync();
+  }
+
   __device__ __forceinline__ void ld(int slot, float (&v)[32]) const { umma::tmem_ld_32x32(tmem + 32u * slot, v); }
   __device__ __forceinline__ void st(int slot, const float (&v)[32]) const { umma::tmem_st_32x32(tmem + 32u * slot, v); }
 };
@@ -202,6 +259,22 @@ __device__ __forceinline__ void store_vec_global(float *p, const float (&v)[32])
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4)
     *reinterpret_cast<float4 *>(p + 4 * k4) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+}
+
+// Coalesced own-row vectors in global memory: vector element block k4 of row r lives at base[(k4 * 128 + r) * 4 .. +4),
+// so one warp-wide 128-bit access covers 512 contiguous bytes (4 lines) instead of 32 different lines.  L2-only
+// (ld/st.global.cg): every value is read back by the thread that wrote it, there is nothing for L1 to share.
+__device__ __forceinline__ void load_vec_global_co(const float *base, int r, float (&v)[32]) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 q = __ldcg(reinterpret_cast<const float4 *>(base + (k4 * kRows + r) * 4));
+    v[4 * k4] = q.x; v[4 * k4 + 1] = q.y; v[4 * k4 + 2] = q.z; v[4 * k4 + 3] = q.w;
+  }
+}
+__device__ __forceinline__ void store_vec_global_co(float *base, int r, const float (&v)[32]) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4)
+    __stcg(reinterpret_cast<float4 *>(base + (k4 * kRows + r) * 4), make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]));
 }
 
 // geometry of one edge from the thread's own and the sender's coordinates (layer input and network input)
