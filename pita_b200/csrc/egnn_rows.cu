@@ -826,6 +826,7 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
   float *scr = team_scr ? team_scr + (size_t)tt * 32 : nullptr;
   auto SCR = [&](int v) { return scr + (size_t)v * kRows * 32; };
   float *escr = team_scr ? team_scr + (size_t)kScrVecs * kRows * 32 : nullptr;
+  asm volatile("" : "+l"(escr));  // opaque: keep the pointer in a register / stack slot instead of re-deriving it from blockIdx
   auto ESCR = [&](int u, int v) { return escr + (size_t)u * kEdgeFloats + (size_t)v * kRows * 32; };  // coalesced block
   auto ESCAL = [&](int u) { return reinterpret_cast<float4 *>(escr + (size_t)u * kEdgeFloats + kEdgeVecs * kRows * 32) + tt; };
 
@@ -1154,6 +1155,16 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
           const float4 yj = c.sX[rj];
           const Geo g = edge_geo4(xi, c.sX[kRows + rj], yi, yj);
           // primal quantities of this edge from the layer-1 edge cache (filled once per tile, before the passes)
+          {  // the cache of all resident teams (237 MB at n = 13) does not stay in L2: pull the next slot in while this one
+             // is being processed (528 lines of 128 B per slot, 4-5 per thread; wraps to slot 0 for the next pass)
+            const int un = (u + 1 < NP - 1) ? u + 1 : 0;
+            const char *nb = reinterpret_cast<const char *>(escr + (size_t)un * kEdgeFloats);
+#pragma unroll
+            for (int i = 0; i < (kEdgeFloats * 4 / 128 + kRows - 1) / kRows; ++i) {
+              const int line = tt + i * kRows;
+              if (line < kEdgeFloats * 4 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (size_t)line * 128));
+            }
+          }
           load_vec_global_co(ESCR(u, 0), tt, f1);
           load_vec_global_co(ESCR(u, 1), tt, m);
           load_vec_global_co(ESCR(u, 2), tt, f2);
@@ -1187,8 +1198,9 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
             }
             if (jk) add_vec(row, sOwnB + (pp * 3 + a) * 32);
             tangent_in(row, f1, vec1, 2.0f * dotD, 2.0f * sgn * e03[a]);
-            T.store_row(row);
-            T.round_trip([&] { T.mma(sAcc0, 1, false); });
+            // TS form: operand row handed over through the row's own TMEM lane (sAccC / sH are free in this loop)
+            T.store_row_tmem(sAccC, sH, row);
+            T.round_trip_ts([&] { T.mma_ts(sAcc0, sAccC, sH, 1, false); });
             T.ld(sAcc0, row);
             tangent_mid(row, m, f2, att, vec1);  // row = d(m*_ij)
             // du = <wc2 * silu'(zc), Wc1 dms> = <v_ij, dms>: a dot product with the cached vector, no MMA
