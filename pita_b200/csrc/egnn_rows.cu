@@ -1227,21 +1227,24 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
             dx2[a][2] += (D2 * g.inv - g.d2 * cg) * phi + g.d2 * g.inv * dphi;
           }
         }
-        // dz3[a] = W3a1 dagg[a] + W3h1 dh^1[a]   (W3a1 / W3h1 sit in slots 3 / 4 of this set)
-#pragma unroll
+        // dz3[a] = W3a1 dagg[a] + W3h1 dh^1[a]   (W3a1 / W3h1 sit in slots 3 / 4 of this set): one round trip per direction,
+        // the aggregate handed over through TMEM (TS form), dh^1 through the shared-memory tile.  The direction loops of
+        // the per-k sections are NOT unrolled (direction-indexed values come from shared memory): this code runs once per
+        // pass and its unrolled size (166 KB) made instruction fetch 37 % of its stalls (profiles/README.md).
+#pragma unroll 1
         for (int a = 0; a < 3; ++a) {
+          const float cfa = comp(sCoef[tt], a);
           T.ld(sT0 + a, row);
-          T.store_row(row);
-          T.round_trip([&] { T.mma(sT0 + a, 3, false); });
+          T.store_row_tmem(sAccC, sH, row);
           if (is_k) {
             load_vec_global(SCR(qDh1o + a), row);
           } else {
             load_vec_global(SCR(qOmega), row);
 #pragma unroll
-            for (int kk = 0; kk < 32; ++kk) row[kk] *= cf[a];
+            for (int kk = 0; kk < 32; ++kk) row[kk] *= cfa;
           }
           T.store_row(row);
-          T.round_trip([&] { T.mma(sT0 + a, 4, true); });
+          T.round_trip([&] { T.mma_ts(sT0 + a, sAccC, sH, 3, false); T.mma(sT0 + a, 4, true); });
         }
       }
       // ---------------- node update of layer 1 on the tangents, then layer 2 on edge (k, i) by the sender's thread
@@ -1269,12 +1272,14 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
         const float th = stage3<true>(row, fc, vec2);
         const float phi = rng * th, dphi_du = rng * (1.0f - th * th);
         const float k2 = g.inv * g.inv / g.nrm;
-        const float dd3[3] = {g.d0, g.d1, g.d2};
-        const float e03[3] = {yk.x - yi.x, yk.y - yi.y, yk.z - yi.z};
-#pragma unroll
+        const float4 dd4 = make_float4(g.d0, g.d1, g.d2, 0.f);
+        const float4 e04 = make_float4(yk.x - yi.x, yk.y - yi.y, yk.z - yi.z, 0.f);
+#pragma unroll 1
         for (int a = 0; a < 3; ++a) {
           float tmp[32];
-          T.ld(sT0 + a, row);  // dz3 = W3a dagg (accumulated over the slots) + W3h dh1
+          const float cfa = comp(sCoef[tt], a), dda = comp(dd4, a), e0a = comp(e04, a);
+          const float4 dxo = sDX[tt * 3 + a];  // this row's own d x^2 [a] (published above)
+          T.ld(sT0 + a, row);  // dz3 = W3a dagg (summed over the slots) + W3h dh1
           load_vec_global(SCR(qF31), tmp);
 #pragma unroll
           for (int kk = 0; kk < 32; ++kk) row[kk] *= tmp[kk];
@@ -1288,7 +1293,7 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
           } else {
             load_vec_global(SCR(qOmega), tmp);
 #pragma unroll
-            for (int kk = 0; kk < 32; ++kk) row[kk] = fmaf(cf[a], tmp[kk], row[kk]);
+            for (int kk = 0; kk < 32; ++kk) row[kk] = fmaf(cfa, tmp[kk], row[kk]);
           }
           T.store_row(row);  // dh^2[a]
           T.round_trip([&] { T.mma(sAccC, 1, false); T.mma(sAcc0, 2, false); });
@@ -1300,9 +1305,9 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
           T.ld(sAcc0, row);  // dQ2_i[a]
           add_vec(row, sKdP2 + (pp * 3 + a) * 32);
           const float4 dxk = sDX[rk * 3 + a];
-          const float D0 = dxk.x - dx2[a][0], D1 = dxk.y - dx2[a][1], D2 = dxk.z - dx2[a][2];
+          const float D0 = dxk.x - dxo.x, D1 = dxk.y - dxo.y, D2 = dxk.z - dxo.z;
           const float dotD = g.d0 * D0 + g.d1 * D1 + g.d2 * D2;
-          tangent_in(row, f1, vec2, 2.0f * dotD, 2.0f * e03[a]);
+          tangent_in(row, f1, vec2, 2.0f * dotD, 2.0f * e0a);
           T.store_row(row);
           T.round_trip([&] { T.mma(sAcc0, 3, false); });
           T.ld(sAcc0, row);
@@ -1312,8 +1317,8 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
           T.ld(sAccC, row);
           const float dphi = dphi_du * tangent_du(row, fc, vec2);
           const float Da = (a == 0) ? D0 : ((a == 1) ? D1 : D2);
-          if (is_k) trace += dx2[a][a];
-          else trace += (Da * g.inv - dd3[a] * dotD * k2) * phi + dd3[a] * g.inv * dphi;
+          if (is_k) trace += comp(dxo, a);
+          else trace += (Da * g.inv - dda * dotD * k2) * phi + dda * g.inv * dphi;
         }
       }
     }

@@ -164,7 +164,7 @@ struct Team {
     if (SPLIT) {
       float h[32], l[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) umma::split_tf32(v[k], h[k], l[k]);
+      for (int k = 0; k < 32; ++k) umma::split_tf32_tangent(v[k], h[k], l[k]);  // (only tangent rows take the TS path)
       umma::tmem_st_32x32(tmem + 32u * slot_hi, h);
       umma::tmem_st_32x32(tmem + 32u * slot_lo, l);
     } else {

@@ -141,5 +141,13 @@ __device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
   lo = round_tf32(a - hi);
 }
 
+// Tangent rows (forward-mode derivative products, which only feed the divergence): hi rounded to nearest, lo = a - hi left
+// to the tensor core's truncation.  |a - hi - trunc(lo)| <= 2^-21 |a| with a sign that follows the (random) sign of lo,
+// i.e. unbiased; 3 instead of 5 integer/float instructions per element.  Primal rows keep split_tf32.
+__device__ __forceinline__ void split_tf32_tangent(float a, float &hi, float &lo) {
+  hi = round_tf32(a);
+  lo = a - hi;
+}
+
 }  // namespace umma
 }  // namespace pita
