@@ -1059,12 +1059,12 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
         node_feats<NP>(k, c_noise, beta, f0k, f1k);
         z1_layer0(row, c.sCls, f0i, f1i, f0k, f1k);
         stage1<true, false>(row, f1, nullptr, 0, vec0, g.r2, g.ea);
-        T.store_row(row);
-        T.round_trip([&] { T.mma(sAcc0, 0, false); });
+        T.store_row_tmem(sH, sP, row);
+        T.round_trip_ts([&] { T.mma_ts(sAcc0, sH, sP, 0, false); });
         T.ld(sAcc0, row);
         const float att = stage2<true>(row, m, f2, vec0);
-        T.store_row(row);
-        T.round_trip([&] { T.mma(sAccC, 1, false); });
+        T.store_row_tmem(sH, sP, row);
+        T.round_trip_ts([&] { T.mma_ts(sAccC, sH, sP, 1, false); });
         T.ld(sAccC, row);
         const float th = stage3<true>(row, fc, vec0);
         const float phi = rng * th, dphi_du = rng * (1.0f - th * th);
@@ -1074,24 +1074,24 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
           row[4 * k4] = f1[4 * k4] * (cc.x + dd.x); row[4 * k4 + 1] = f1[4 * k4 + 1] * (cc.y + dd.y);
           row[4 * k4 + 2] = f1[4 * k4 + 2] * (cc.z + dd.z); row[4 * k4 + 3] = f1[4 * k4 + 3] * (cc.w + dd.w);
         }
-        T.store_row(row);
-        T.round_trip([&] { T.mma(sAcc0, 0, false); });
+        T.store_row_tmem(sH, sP, row);
+        T.round_trip_ts([&] { T.mma_ts(sAcc0, sH, sP, 0, false); });
         T.ld(sAcc0, row);
         tangent_mid(row, m, f2, att, vec0);  // wvec_ik
-        T.store_row(row);
-        T.round_trip([&] { T.mma(sAccC, 1, false); T.mma(sAcc0, 2, false); });
+        T.store_row_tmem(sH, sP, row);
+        T.round_trip_ts([&] { T.mma_ts(sAccC, sH, sP, 1, false); T.mma_ts(sAcc0, sH, sP, 2, false); });
         T.ld(sAccC, row);
         const float du_base = tangent_du(row, fc, vec0);
         T.ld(sAcc0, row);
         load_vec_global(SCR(qF30), f1);
 #pragma unroll
         for (int kk = 0; kk < 32; ++kk) row[kk] *= f1[kk];
-        T.store_row(row);
-        T.round_trip([&] { T.mma(sAcc0, 3, false); });
+        T.store_row_tmem(sH, sP, row);
+        T.round_trip_ts([&] { T.mma_ts(sAcc0, sH, sP, 3, false); });
         T.ld(sAcc0, row);  // omega_ik
         store_vec_global(SCR(qOmega), row);
-        T.store_row(row);
-        T.round_trip([&] { T.mma(sPA, 4, false); });  // piA_ik = A1 omega -> its TMEM slot (piB follows once B1 is loaded)
+        T.store_row_tmem(sH, sP, row);
+        T.round_trip_ts([&] { T.mma_ts(sPA, sH, sP, 4, false); });  // piA_ik = A1 omega -> its TMEM slot (piB follows once B1 is loaded)
         const float dd3[3] = {g.d0, g.d1, g.d2};
         if (!is_k) {
           const float k2 = g.inv * g.inv / g.nrm;
@@ -1130,7 +1130,7 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
       // ---------------- layer 1 (dense)
       load_weights(c, setB);
       if (team_active) {  // piB_ik = B1 omega (the A tile still holds the omega rows)
-        T.round_trip([&] { T.mma(sAcc0, 0, false); });
+        T.round_trip_ts([&] { T.mma_ts(sAcc0, sH, sP, 0, false); });
         T.ld(sAcc0, row);
         if (is_k) {
 #pragma unroll
@@ -1198,9 +1198,9 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
             }
             if (jk) add_vec(row, sOwnB + (pp * 3 + a) * 32);
             tangent_in(row, f1, vec1, 2.0f * dotD, 2.0f * sgn * e03[a]);
-            // TS form: operand row handed over through the row's own TMEM lane (sAccC / sH are free in this loop)
-            T.store_row_tmem(sAccC, sH, row);
-            T.round_trip_ts([&] { T.mma_ts(sAcc0, sAccC, sH, 1, false); });
+            // TS form: operand row handed over through the row's own TMEM lane (slots sH / sP are free during the passes)
+            T.store_row_tmem(sH, sP, row);
+            T.round_trip_ts([&] { T.mma_ts(sAcc0, sH, sP, 1, false); });
             T.ld(sAcc0, row);
             tangent_mid(row, m, f2, att, vec1);  // row = d(m*_ij)
             // du = <wc2 * silu'(zc), Wc1 dms> = <v_ij, dms>: a dot product with the cached vector, no MMA
@@ -1235,7 +1235,7 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
         for (int a = 0; a < 3; ++a) {
           const float cfa = comp(sCoef[tt], a);
           T.ld(sT0 + a, row);
-          T.store_row_tmem(sAccC, sH, row);
+          T.store_row_tmem(sH, sP, row);
           if (is_k) {
             load_vec_global(SCR(qDh1o + a), row);
           } else {
@@ -1244,7 +1244,7 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
             for (int kk = 0; kk < 32; ++kk) row[kk] *= cfa;
           }
           T.store_row(row);
-          T.round_trip([&] { T.mma_ts(sT0 + a, sAccC, sH, 3, false); T.mma(sT0 + a, 4, true); });
+          T.round_trip([&] { T.mma_ts(sT0 + a, sH, sP, 3, false); T.mma(sT0 + a, 4, true); });
         }
       }
       // ---------------- node update of layer 1 on the tangents, then layer 2 on edge (k, i) by the sender's thread
@@ -1262,12 +1262,12 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
 #pragma unroll
         for (int kk = 0; kk < 32; ++kk) row[kk] += f1[kk];
         stage1<true, false>(row, f1, nullptr, 0, vec2, g.r2, g.ea);
-        T.store_row(row);
-        T.round_trip([&] { T.mma(sAcc0, 3, false); });
+        T.store_row_tmem(sH, sP, row);
+        T.round_trip_ts([&] { T.mma_ts(sAcc0, sH, sP, 3, false); });
         T.ld(sAcc0, row);
         const float att = stage2<true>(row, m, f2, vec2);
-        T.store_row(row);
-        T.round_trip([&] { T.mma(sAccC, 4, false); });
+        T.store_row_tmem(sH, sP, row);
+        T.round_trip_ts([&] { T.mma_ts(sAccC, sH, sP, 4, false); });
         T.ld(sAccC, row);
         const float th = stage3<true>(row, fc, vec2);
         const float phi = rng * th, dphi_du = rng * (1.0f - th * th);
@@ -1283,8 +1283,8 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
           load_vec_global(SCR(qF31), tmp);
 #pragma unroll
           for (int kk = 0; kk < 32; ++kk) row[kk] *= tmp[kk];
-          T.store_row(row);
-          T.round_trip([&] { T.mma(sAcc0, 0, false); });
+          T.store_row_tmem(sH, sP, row);
+          T.round_trip_ts([&] { T.mma_ts(sAcc0, sH, sP, 0, false); });
           T.ld(sAcc0, row);
           if (is_k) {
             load_vec_global(SCR(qDh1o + a), tmp);
@@ -1295,8 +1295,8 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
 #pragma unroll
             for (int kk = 0; kk < 32; ++kk) row[kk] = fmaf(cfa, tmp[kk], row[kk]);
           }
-          T.store_row(row);  // dh^2[a]
-          T.round_trip([&] { T.mma(sAccC, 1, false); T.mma(sAcc0, 2, false); });
+          T.store_row_tmem(sH, sP, row);  // dh^2[a]
+          T.round_trip_ts([&] { T.mma_ts(sAccC, sH, sP, 1, false); T.mma_ts(sAcc0, sH, sP, 2, false); });
           T.ld(sAccC, tmp);  // (tcgen05.ld is warp-collective: never inside a divergent branch)
           if (is_k) store_vec_smem(sKdP2 + (pp * 3 + a) * 32, tmp);
           umma::fence_before_thread_sync();
@@ -1308,12 +1308,12 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
           const float D0 = dxk.x - dxo.x, D1 = dxk.y - dxo.y, D2 = dxk.z - dxo.z;
           const float dotD = g.d0 * D0 + g.d1 * D1 + g.d2 * D2;
           tangent_in(row, f1, vec2, 2.0f * dotD, 2.0f * e0a);
-          T.store_row(row);
-          T.round_trip([&] { T.mma(sAcc0, 3, false); });
+          T.store_row_tmem(sH, sP, row);
+          T.round_trip_ts([&] { T.mma_ts(sAcc0, sH, sP, 3, false); });
           T.ld(sAcc0, row);
           tangent_mid(row, m, f2, att, vec2);
-          T.store_row(row);
-          T.round_trip([&] { T.mma(sAccC, 4, false); });
+          T.store_row_tmem(sH, sP, row);
+          T.round_trip_ts([&] { T.mma_ts(sAccC, sH, sP, 4, false); });
           T.ld(sAccC, row);
           const float dphi = dphi_du * tangent_du(row, fc, vec2);
           const float Da = (a == 0) ? D0 : ((a == 1) ? D1 : D2);
