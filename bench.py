@@ -28,6 +28,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: LJ-55, 256k-4M particles sharded across 1/2/4/8 B200
     "lj55": dict(n=55, particles=1 << 18, chunk=512, sigma_min=0.05, label="LJ-55 annealed FK sampling, 256k particles/GPU (BASELINE configs[2])"),
 }
+# measured by ncu on this kernel (bytes per particle per launch; see profiles/README.md); filled from the round's last capture
+NCU_DRAM_BYTES_PER_PARTICLE = {13: (50.237704e9 + 5.881976e9) / 37888,   # profiles/r1n_ncu_scorediv13.txt (37 888 particles)
+                               55: (496.511952e9 + 13.595801e9) / 4736}   # profiles/r1n_ncu_scorediv55.txt (4 736 particles)
 GAMMA = 4.0 / 3.0  # beta_lower / beta for the 4.0 -> 3.0 rung of the temperature ladder (lj13.yaml:44-50)
 BETA = 0.75
 T_STEP = 0.5       # SDE time at which the timed steps are evaluated
@@ -139,10 +142,12 @@ def run_reference(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("PITA_BENCH_WORKLOAD", "lj13"), choices=sorted(WORKLOADS))
+    # BASELINE.json's metric is quoted on LJ-55 (configs[2], 256k particles per GPU at the low end of its 256k-4M range, which
+    # fits one GPU); --workload lj13 runs configs[1] (LJ-13, 2^20 particles)
+    ap.add_argument("--workload", default=os.environ.get("PITA_BENCH_WORKLOAD", "lj55"), choices=sorted(WORKLOADS))
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's)")
     ap.add_argument("--cpu-particles", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -219,7 +224,7 @@ def main():
     ht = torch.full((Nl,), float(sched.h(torch.tensor(T_STEP, dtype=torch.float64))), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     kt = []
-    for _ in range(3):
+    for _ in range(3 if n == 13 else 2):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -227,7 +232,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         kt.append(e0.elapsed_time(e1))
-    k_ms = sorted(kt)[1]
+    k_ms = sorted(kt)[len(kt) // 2] if len(kt) > 2 else min(kt)
     alg_flops = (3 * n + 1) * 2.0 * egnn_macs_forward(n) * Nl  # (3n+1) forward-equivalents per particle
     peaks = {}
     try:
@@ -236,11 +241,32 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved_tf = alg_flops / (k_ms * 1e-3) / 1e12
+    # DRAM traffic of this kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum), captured on a smaller
+    # launch of the same kernel and scaled per particle (profiles/README.md names the capture); None if never captured
+    traffic = NCU_DRAM_BYTES_PER_PARTICLE.get(n)
     roofline = {"kernel": "egnn_score_div_rows_kernel (%s)" % ops.default_div_mode(), "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None, "kernel_ms": k_ms,
+                "frac": achieved_tf / peak_tf, "traffic": None if traffic is None else traffic * Nl, "kernel_ms": k_ms,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
                 "note": "algorithmic FLOPs = (3n+1) dense EGNN forwards per particle (SURVEY 8d); the kernel executes ~21 (n=13) / ~76 (n=55) "
                         "forward-equivalents (structured tangents) as tcgen05 kind::tf32 MMAs (x3 in 3xtf32 mode) against the bf16 peak"}
+
+    # ---- second half of BASELINE.json's metric: the Lennard-Jones energy+force kernel as a fraction of the FP32 FMA peak
+    #      (31 FLOP per unordered pair + 15 per atom), timed alone on this rank's particles, L2 flushed
+    lj_t = []
+    for _ in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.lj_energy_force(x, n)
+        e1.record()
+        torch.cuda.synchronize()
+        lj_t.append(e0.elapsed_time(e1))
+    lj_ms = sorted(lj_t)[2]
+    fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+    lj_tf = (31 * n * (n - 1) // 2 + 15 * n) * Nl / (lj_ms * 1e-3) / 1e12
+    lj_kernel = {"kernel": "lj_pairs_kernel", "configs_per_s": Nl / (lj_ms * 1e-3), "ms": lj_ms, "alg_tflops": lj_tf,
+                 "fp32_peak_tflops": fp32_peak, "frac_fp32_peak": lj_tf / fp32_peak,
+                 "alg_gbs": (8 * D + 4) * Nl / (lj_ms * 1e-3) / 1e9}
 
     # ---- end to end through the public step with HOST buffers: H2D of (x, a), one FK step, D2H of (x', a')
     hx = torch.empty(Nl, D, pin_memory=True).copy_(x.cpu())
@@ -262,7 +288,9 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = N * KE / (float(e2e_ms.item()) * 1e-3)
-    launches_per_step = 4 + 7 + (1 if not args.fused_noise else 0)  # ours: energy, score_div, sde_step, quantile + resample(7)
+    # our kernels per step (profiles/r1d_launches_lj13.csv): energy, score_div, sde_fk_step, fk_quantile + resampling (softmax
+    # partials / finalize / clip, scan tile sums / offsets / bins, search, change count, gather) = 13; torch's randn / fills not counted
+    launches_per_step = 4 + 9
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -283,7 +311,7 @@ def main():
                            "exchange": integ._resampler.exchange},
                 "clocks": clk, "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": Nl * D * 4 + Nl * 4,
                                        "d2h_bytes_per_step": Nl * D * 4 + Nl * 4},
-                "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "gpu_launches": launches_per_step * K, "roofline": roofline, "lj_kernel": lj_kernel, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
