@@ -677,9 +677,6 @@ int launch_energy_rows(int n, bool split, const float *w, const float *ht, const
 int64_t score_div_rows_workspace_bytes(int n);
 int launch_score_div_rows(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,
                           float *sc, float *dv, float *scratch, int64_t scratch_bytes, cudaStream_t s);
-int64_t score_div_mma_workspace_bytes(int n);
-int launch_score_div_mma(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,
-                         float *sc, float *dv, float *scratch, int64_t scratch_bytes, cudaStream_t s);
 }  // namespace pita
 
 using namespace pita;
