@@ -143,3 +143,14 @@ def import_reference():
     ns.prior = importlib.import_module("src.energies.base_prior")
     ns.lj = importlib.import_module("src.energies.lennardjones_energy")
     return ns
+
+
+def import_reference_ad2():
+    """The alanine-dipeptide EGNN (egnn_dynamics_ad2_cat.py; SURVEY §8 row a8').  Its module imports mdtraj at the top
+    (:3) only to read a topology for the >= 53-atom systems; a bare stub is enough for the 22-atom network."""
+    import importlib
+
+    import_reference()
+    if "mdtraj" not in sys.modules:
+        _mod("mdtraj")
+    return importlib.import_module("src.models.components.egnn_dynamics_ad2_cat")

@@ -249,9 +249,44 @@ def golden_loop():
         torch.set_default_dtype(torch.float32)
 
 
+def golden_ad2():
+    """Alanine-dipeptide EGNN (SURVEY §8 row a8'): EGNN_dynamics_AD2_cat, 22 atoms, hidden 64, 5 layers, condition_beta,
+    random init (seed 12345) with the coordinate gain raised like the LJ "strong" fixtures; weights are rounded to fp32 for
+    the fixture and the reference is evaluated in fp64 FROM those rounded weights."""
+    from _ref_import import import_reference_ad2
+    ad2 = import_reference_ad2()
+    n, B = 22, 6
+    torch.manual_seed(12345)
+    net = ad2.EGNN_dynamics_AD2_cat(n_particles=n, n_dimensions=3, hidden_nf=64, n_layers=5, act_fn=torch.nn.SiLU(),
+                                    recurrent=True, attention=True, tanh=True, agg="sum", condition_beta=True)
+    with torch.no_grad():
+        for l in range(5):
+            getattr(net.egnn, f"gcl_{l}").coord_mlp[2].weight.mul_(300.0)
+    net = net.double()
+    with torch.no_grad():
+        for p_ in net.parameters():
+            p_.copy_(p_.float().double())
+    gen = torch.Generator().manual_seed(22)
+    # MD-shaped synthetic coordinates in the reference's normalised units (SURVEY §8d: lattice recipe / 0.164-style scale)
+    side = 3
+    sites = torch.stack(torch.meshgrid(*[torch.arange(side, dtype=torch.float64)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n] * 1.1
+    x = sites.reshape(1, 3 * n).repeat(B, 1) + 0.08 * torch.randn(B, 3 * n, generator=gen, dtype=torch.float64)
+    x = (x.reshape(B, n, 3) - x.reshape(B, n, 3).mean(1, keepdim=True)).reshape(B, 3 * n)
+    t = torch.linspace(0.05, 0.95, B, dtype=torch.float64)
+    beta = torch.full((B,), 1.25, dtype=torch.float64)
+    with torch.no_grad():
+        vel = net(t, x, beta)
+    out = {"n": n, "x": x.numpy(), "t": t.numpy(), "beta": beta.numpy(), "vel": vel.numpy()}
+    out.update({"W." + k: v.detach().float().numpy() for k, v in net.state_dict().items()})
+    np.savez_compressed(os.path.join(OUT, "egnn_ad2_n22.npz"), **out)
+    print("wrote ad2", float(vel.abs().max()))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["resample", "lj", "fk", "loop"]
+    which = sys.argv[1:] or ["resample", "lj", "fk", "loop", "ad2"]
+    if "ad2" in which:
+        golden_ad2()
     if "resample" in which:
         golden_resample()
     if "lj" in which:

@@ -158,7 +158,7 @@ def egnn_layer_count(sd: Dict[str, Tensor]) -> int:
 
 
 def egnn_velocity(sd: Dict[str, Tensor], tcond: Tensor, y: Tensor, beta: Tensor, n: int,
-                  coords_range: float = 15.0, skip_dead: bool = False) -> Tensor:
+                  coords_range: float = 15.0, skip_dead: bool = False, node_feat: Optional[Tensor] = None) -> Tensor:
     """EGNN_dynamics.forward (egnn_temp_conditioned.py:56-93) with condition_time and
     condition_temperature, recurrent, tanh, attention, agg='sum', norm_diff (the configuration of
     configs/model/net/egnn_temp.yaml).  tcond, beta: [B]; y: [B, 3n] -> [B, 3n].
@@ -175,7 +175,7 @@ def egnn_velocity(sd: Dict[str, Tensor], tcond: Tensor, y: Tensor, beta: Tensor,
     # f = (t,...,t, beta,...,beta): the first n//2 nodes see (t,t), the last n//2 see (beta,beta)
     # and (for odd n) the middle node sees (t,beta).  Reproduced verbatim — parity requires it.
     flat = torch.cat([tcond[:, None].expand(B, n), beta[:, None].expand(B, n)], dim=-1)  # [B,2n]
-    feat = flat.reshape(B, n, 2)
+    feat = flat.reshape(B, n, 2) if node_feat is None else node_feat  # node_feat: [B,n,F] (egnn_velocity_ad2)
     h = feat @ sd["egnn.embedding.weight"].T + sd["egnn.embedding.bias"]  # [B,n,H] (:179)
     off = ~torch.eye(n, dtype=torch.bool)
     offf = off.to(y.dtype)[None, :, :, None]
@@ -209,6 +209,33 @@ def egnn_velocity(sd: Dict[str, Tensor], tcond: Tensor, y: Tensor, beta: Tensor,
     vel = x - x0
     vel = vel - vel.mean(dim=1, keepdim=True)  # (:84)
     return vel.reshape(B, n * 3)
+
+
+def ad2_atom_types(n: int = 22) -> Tensor:
+    """EGNN_dynamics_AD2_cat.get_h_initial for alanine dipeptide (egnn_dynamics_ad2_cat.py:67-73): one class per
+    atom except the three hydrogen triples that share a class; the largest label is 20, so one_hot has 21 columns."""
+    if n != 22:
+        raise NotImplementedError("only the 22-atom alanine dipeptide typing is restated")
+    t = torch.arange(22)
+    t[[0, 2, 3]] = 2
+    t[[19, 20, 21]] = 20
+    t[[11, 12, 13]] = 12
+    return t
+
+
+def egnn_velocity_ad2(sd: Dict[str, Tensor], t: Tensor, y: Tensor, beta: Tensor, n: int = 22,
+                      condition_beta: bool = True, coords_range: float = 15.0) -> Tensor:
+    """EGNN_dynamics_AD2_cat.forward (egnn_dynamics_ad2_cat.py:158-194) over egnn.EGNN (egnn.py:108-184): the same E_GCL
+    stack as egnn_velocity (recurrent, tanh, attention, agg='sum'; H and L read from the weights: 64 / 5 in
+    configs/model/net/egnn_ad2.yaml-style use), but every node carries one_hot(atom type) ++ [t] (++ [beta]) — here the
+    time / temperature columns really are per node (:176-186), unlike the interleaving quirk of the LJ network.
+    SURVEY §8 row a8'.  TEST INFRASTRUCTURE: the CUDA path for this network is not built yet."""
+    B = y.shape[0]
+    onehot = torch.nn.functional.one_hot(ad2_atom_types(n)).to(y.dtype)  # [n, 21]
+    cols = [onehot[None].expand(B, n, onehot.shape[1]), t[:, None, None].expand(B, n, 1)]
+    if condition_beta:
+        cols.append(beta[:, None, None].expand(B, n, 1))
+    return egnn_velocity(sd, t, y, beta, n, coords_range=coords_range, node_feat=torch.cat(cols, dim=-1))
 
 
 # --------------------------------------------------------------------------------------

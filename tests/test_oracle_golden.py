@@ -122,3 +122,20 @@ def test_loop_matches_reference(golden_dir):
     assert list(uniq) == list(g["num_unique"])
     _close(logw, g["logweights"], 1e-8, "logweights")
     _close(x, g["x_final"], 1e-8, "x_final")
+
+
+def test_ad2_egnn_oracle_vs_reference_golden(golden_dir):
+    """SURVEY §8 row a8' (alanine dipeptide EGNN: 22 atoms, hidden 64, 5 layers, 21 one-hot node-type columns ++ t ++ beta): the oracle
+    restatement reproduces the unmodified reference's forward (fixture generated by oracle/make_golden.py ad2) in fp64.
+    The CUDA path for this network is not built yet — this pins the oracle for it."""
+    g = _load(golden_dir, "egnn_ad2_n22.npz")
+    sd = _sd(g, "W.")
+    n = int(g["n"])
+    assert O.egnn_layer_count(sd) == 5 and sd["egnn.embedding.weight"].shape == (64, 23)
+    vel = O.egnn_velocity_ad2(sd, torch.from_numpy(g["t"]), torch.from_numpy(g["x"]), torch.from_numpy(g["beta"]), n)
+    ref = torch.from_numpy(g["vel"])
+    assert (vel - ref).abs().max().item() <= 1e-12 * max(1.0, ref.abs().max().item())
+    # the node-type table (egnn_dynamics_ad2_cat.py:67-73): three hydrogen triples share a class; the largest label is 20,
+    # so one_hot has 21 columns and in_node_nf = 21 + t + beta = 23
+    types = O.ad2_atom_types(22)
+    assert types.max().item() == 20 and len(set(types.tolist())) == 16
