@@ -1148,24 +1148,16 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
         for (int b = 0; b < 3; ++b) dx2[a][b] = dxi[a][b];
       if (team_active) {
         const float4 xi = c.sX[kRows + tt];
-        // software pipeline over the sender slots: the cache vectors of slot u + 1 are requested right after the last use
-        // of slot u's copy (same registers), so their L2 latency is covered by the rest of the iteration
-        load_vec_global_co(ESCR(0, 0), tt, f1);
-        load_vec_global_co(ESCR(0, 1), tt, m);
-        load_vec_global_co(ESCR(0, 2), tt, f2);
-        load_vec_global_co(ESCR(0, 3), tt, fc);  // fc <- v_ij = Wc1^T (wc2 * silu'(zc))
-        float4 sc4 = __ldcg(ESCAL(0));
 #pragma unroll 1
         for (int u = 0; u < NP - 1; ++u) {
           const int j = c.sender(u), rj = pp * NP + j;
           const bool jk = (j == k);
-          const bool more = u + 1 < NP - 1;
           const float4 yj = c.sX[rj];
           const Geo g = edge_geo4(xi, c.sX[kRows + rj], yi, yj);
           // primal quantities of this edge from the layer-1 edge cache (filled once per tile, before the passes)
           {  // the cache of all resident teams (237 MB at n = 13) does not stay in L2: pull the next slot in while this one
-             // is being processed (528 lines of 128 B per slot, 4-5 per thread; two slots ahead, wrapping into the next pass)
-            const int un = (u + 2 < NP - 1) ? u + 2 : u + 2 - (NP - 1);
+             // is being processed (528 lines of 128 B per slot, 4-5 per thread; wraps to slot 0 for the next pass)
+            const int un = (u + 1 < NP - 1) ? u + 1 : 0;
             const char *nb = reinterpret_cast<const char *>(escr + (size_t)un * kEdgeFloats);
 #pragma unroll
             for (int i = 0; i < (kEdgeFloats * 4 / 128 + kRows - 1) / kRows; ++i) {
@@ -1173,8 +1165,12 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
               if (line < kEdgeFloats * 4 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (size_t)line * 128));
             }
           }
+          load_vec_global_co(ESCR(u, 0), tt, f1);
+          load_vec_global_co(ESCR(u, 1), tt, m);
+          load_vec_global_co(ESCR(u, 2), tt, f2);
+          load_vec_global_co(ESCR(u, 3), tt, fc);  // fc <- v_ij = Wc1^T (wc2 * silu'(zc))
+          const float4 sc4 = __ldcg(ESCAL(u));
           const float att = sc4.x, th = sc4.y;
-          if (more) sc4 = __ldcg(ESCAL(u + 1));
           const float phi = rng * th, dphi_du = rng * (1.0f - th * th);
           const float k2 = g.inv * g.inv / g.nrm;
           const float4 cfj = sCoef[rj];
@@ -1202,21 +1198,15 @@ egnn_score_div_rows_kernel(const float *__restrict__ wpack, const float *__restr
             }
             if (jk) add_vec(row, sOwnB + (pp * 3 + a) * 32);
             tangent_in(row, f1, vec1, 2.0f * dotD, 2.0f * sgn * e03[a]);
-            if (a == 2 && more) load_vec_global_co(ESCR(u + 1, 0), tt, f1);
             // TS form: operand row handed over through the row's own TMEM lane (slots sH / sP are free during the passes)
             T.store_row_tmem(sH, sP, row);
             T.round_trip_ts([&] { T.mma_ts(sAcc0, sH, sP, 1, false); });
             T.ld(sAcc0, row);
             tangent_mid(row, m, f2, att, vec1);  // row = d(m*_ij)
-            if (a == 2 && more) {
-              load_vec_global_co(ESCR(u + 1, 1), tt, m);
-              load_vec_global_co(ESCR(u + 1, 2), tt, f2);
-            }
             // du = <wc2 * silu'(zc), Wc1 dms> = <v_ij, dms>: a dot product with the cached vector, no MMA
             float du = 0.f;
 #pragma unroll
             for (int kk = 0; kk < 32; ++kk) du = fmaf(fc[kk], row[kk], du);
-            if (a == 2 && more) load_vec_global_co(ESCR(u + 1, 3), tt, fc);
             const float dphi = dphi_du * du;
             // d agg_i[a] += dms: summed in fp32 (round-to-nearest) in the row's own TMEM lane; W3a is applied once per
             // direction after the slots (linearity) instead of one accumulating MMA per edge
