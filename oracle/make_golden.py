@@ -249,6 +249,35 @@ def golden_loop():
         torch.set_default_dtype(torch.float32)
 
 
+def golden_laplacian():
+    """No-score-net branch of VEReverseSDE.f (sdes.py:150-153, 204-216): b = -grad U g^2/2 and
+    div b = -laplacian(U) g^2/2 through compute_laplacian_exact.  LJ-13, strong coordinate gain, fp64."""
+    n, B, t, beta = 13, 4, 0.37, 0.75
+    net_e = make_net(n, 12345, True)
+    gen = torch.Generator().manual_seed(1313)
+    sched = ref.noise.ElucidatingNoiseSchedule(sigma_min=0.05, sigma_max=80, rho=7)
+    x32 = O.md_shaped_coords(B, n, seed=20) * (1.0 + float(sched.h(torch.tensor(t))) ** 0.5 * 0.3)
+    x32 = ref.data_utils.remove_mean(x32 + 0.3 * torch.randn(B, 3 * n, generator=gen), n, 3)
+    out = {"n": n, "t": t, "beta": beta, "x": x32.double().numpy(), "sigma_min": 0.05, "gamma": 4.0 / 3.0}
+    out.update(sd_np(net_e, "E."))
+    torch.set_default_dtype(torch.float64)
+    try:
+        en = ref.energy_net.EnergyNet(net_e.double())
+        sde = ref.sdes.VEReverseSDE(sched, energy_net=en, score_net=None, pin_energy=False, debias_inference=True,
+                                    cdf=lambda *a: None)  # (the constructor dereferences score_net.forward when cdf is None, sdes.py:113)
+        sde.trainer = FakeTrainer()
+        gs = ref.anneal.ConstantAnnealingFactorSchedule(4.0 / 3.0)
+        terms = sde.f(torch.tensor(t), x32.double().clone(), torch.tensor(beta), gs, 1.0, None, resampling_interval=1)
+        out["drift_X"] = terms.drift_X.detach().numpy()
+        out["drift_A"] = terms.drift_A.detach().numpy()
+        out["div_b"] = terms.divergence_score.detach().numpy()
+        out["cross"] = terms.cross_term.detach().numpy()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(OUT, "fk_n13_laplacian.npz"), **out)
+    print("wrote laplacian", out["div_b"])
+
+
 def golden_ad2():
     """Alanine-dipeptide EGNN (SURVEY §8 row a8'): EGNN_dynamics_AD2_cat, 22 atoms, hidden 64, 5 layers, condition_beta,
     random init (seed 12345) with the coordinate gain raised like the LJ "strong" fixtures; weights are rounded to fp32 for
@@ -284,7 +313,9 @@ def golden_ad2():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["resample", "lj", "fk", "loop", "ad2"]
+    which = sys.argv[1:] or ["resample", "lj", "fk", "loop", "ad2", "laplacian"]
+    if "laplacian" in which:
+        golden_laplacian()
     if "ad2" in which:
         golden_ad2()
     if "resample" in which:

@@ -282,6 +282,18 @@ def exact_divergence(fn: Callable[[Tensor, Tensor], Tensor], ht: Tensor, x: Tens
     return jac.diagonal(dim1=-2, dim2=-1).sum(-1).detach()
 
 
+def exact_laplacian(fn: Callable[[Tensor, Tensor], Tensor], ht: Tensor, x: Tensor) -> Tensor:
+    """utils.py:68-77 (compute_laplacian_exact): per-sample Hessian of a scalar field by vmap(hessian), then its trace.
+    fn(h[1], x[1, D]) -> [1]."""
+    from torch.func import hessian, vmap
+
+    def one(h1, x1):
+        return fn(h1[None], x1[None])[0]
+
+    hes = vmap(hessian(one, argnums=1))(ht, x)
+    return hes.diagonal(dim1=-2, dim2=-1).sum(-1).detach()
+
+
 # --------------------------------------------------------------------------------------
 # FK drift (VEReverseSDE.f) and diffusion
 # --------------------------------------------------------------------------------------
@@ -305,7 +317,8 @@ def quantile_clamp(v: Tensor, q: float = 0.9) -> Tensor:
 
 def fk_drift(sd_energy, sd_score, sched: EDMSchedule, gamma_sched, t: float, x: Tensor, beta: float,
              n: int, debias: bool = True) -> Drift:
-    """VEReverseSDE.f for one chunk (sdes.py:130-239); score_net present, pin_energy False."""
+    """VEReverseSDE.f for one chunk (sdes.py:130-239), pin_energy False; sd_score=None is the no-score-net (Laplacian)
+    branch (oracle only — the CUDA path raises NotImplementedError for it)."""
     B = x.shape[0]
     tt = torch.full((B,), float(t), dtype=x.dtype)
     gam = gamma_sched.gamma(tt)
@@ -319,13 +332,17 @@ def fk_drift(sd_energy, sd_score, sched: EDMSchedule, gamma_sched, t: float, x: 
         ht = sched.h(tr)
         u = model_energy(sd_energy, ht, xr, beta, n)
         grad_u, du_dt = torch.autograd.grad(u.sum(), (xr, tr))
-        s = model_score(sd_score, ht, xr, beta, n).detach()
+        s = None if sd_score is None else model_score(sd_score, ht, xr, beta, n).detach()
     ht = ht.detach()
     u = u.detach()
-    b = s * g2[:, None] / 2
+    if sd_score is None:  # no score net (sdes.py:150-153, 204-216): b = -grad U g^2/2, div b = -laplacian(U) g^2/2
+        b = -grad_u * g2[:, None] / 2
+        div_b = -exact_laplacian(lambda h1, x1: model_energy(sd_energy, h1, x1, beta, n), ht, x.detach()) * g2 / 2
+    else:
+        b = s * g2[:, None] / 2
+        div_s = exact_divergence(lambda h1, x1: model_score(sd_score, h1, x1, beta, n), ht, x.detach())
+        div_b = div_s * g2 / 2
     drift_x = gam[:, None] * (-grad_u) * g2[:, None] / 2 + gam[:, None] * b
-    div_s = exact_divergence(lambda h1, x1: model_score(sd_score, h1, x1, beta, n), ht, x.detach())
-    div_b = div_s * g2 / 2
     cross = (-grad_u * b).sum(-1)
     raw = gam * gam * cross + gam * div_b + gam * du_dt + gamma_sched.dgamma_dt(tt) * u
     return Drift(drift_x=drift_x, drift_a=quantile_clamp(raw), div_b=div_b, cross=cross, du_dt=du_dt,

@@ -139,3 +139,17 @@ def test_ad2_egnn_oracle_vs_reference_golden(golden_dir):
     # so one_hot has 21 columns and in_node_nf = 21 + t + beta = 23
     types = O.ad2_atom_types(22)
     assert types.max().item() == 20 and len(set(types.tolist())) == 16
+
+
+def test_laplacian_branch_oracle_vs_reference_golden(golden_dir):
+    """VEReverseSDE.f without a score net (b = -grad U g^2/2, div b = -laplacian(U) g^2/2 through
+    compute_laplacian_exact, sdes.py:150-153, 204-216).  Oracle vs the unmodified reference in fp64 (fixture:
+    oracle/make_golden.py laplacian).  The CUDA path raises NotImplementedError for this branch; this pins its oracle."""
+    g = _load(golden_dir, "fk_n13_laplacian.npz")
+    n = int(g["n"])
+    d = O.fk_drift(_sd(g, "E."), None, O.EDMSchedule(float(g["sigma_min"])), O.ConstGamma(float(g["gamma"])), float(g["t"]),
+                   torch.from_numpy(g["x"]), float(g["beta"]), n)
+    _close(d.div_b, g["div_b"], 1e-9, "div_b (laplacian)")
+    _close(d.cross, g["cross"], 1e-9, "cross term")
+    _close(d.drift_x, g["drift_X"], 1e-9, "drift_X")
+    _close(d.drift_a, g["drift_A"], 1e-9, "drift_A")
