@@ -249,6 +249,28 @@ def golden_loop():
         torch.set_default_dtype(torch.float32)
 
 
+def golden_schedules():
+    """Noise schedules (noise_schedules.py:19-28, 64-125) and annealing-factor schedules (annealing_factor_schedules.py:20-109)
+    of the reference on a grid of times, fp64 — pins the host-side mirrors in pita_b200/ and the oracle's restatements."""
+    t = torch.linspace(0.0, 1.0, 41, dtype=torch.float64)
+    out = {"t": t.numpy()}
+    for tag, sch in (("edm005", ref.noise.ElucidatingNoiseSchedule(0.05, 80, 7)), ("edm001", ref.noise.ElucidatingNoiseSchedule(0.01, 80, 7)),
+                     ("geo", ref.noise.GeometricNoiseSchedule(0.01, 3.0)), ("lin", ref.noise.LinearNoiseSchedule(2.5))):
+        out[tag + ".h"] = torch.as_tensor(sch.h(t), dtype=torch.float64).numpy()
+        out[tag + ".g"] = torch.as_tensor(sch.g(t), dtype=torch.float64).numpy()
+        if hasattr(sch, "dh_dt"):
+            out[tag + ".dh_dt"] = torch.as_tensor(sch.dh_dt(t), dtype=torch.float64).numpy()
+        if hasattr(sch, "t"):
+            out[tag + ".t_of_h"] = torch.as_tensor(sch.t(sch.h(t)), dtype=torch.float64).numpy()
+    for tag, sch in (("const", ref.anneal.ConstantAnnealingFactorSchedule(4.0 / 3.0)),
+                     ("linear", ref.anneal.LinearAnnealingFactorSchedule(1.5, 1.0, t_start=0.8, t_end=0.2)),
+                     ("sigmoid", ref.anneal.SigmoidAnnealingFactorSchedule(1.5, 1.0, t_start=0.9, t_end=0.1, sharpness=8.0))):
+        out[tag + ".gamma"] = torch.as_tensor(sch.gamma(t), dtype=torch.float64).numpy()
+        out[tag + ".dgamma_dt"] = torch.as_tensor(sch.dgamma_dt(t), dtype=torch.float64).numpy()
+    np.savez_compressed(os.path.join(OUT, "schedules.npz"), **out)
+    print("wrote schedules", {k: v.shape for k, v in out.items() if k.endswith(".h")})
+
+
 def golden_laplacian():
     """No-score-net branch of VEReverseSDE.f (sdes.py:150-153, 204-216): b = -grad U g^2/2 and
     div b = -laplacian(U) g^2/2 through compute_laplacian_exact.  LJ-13, strong coordinate gain, fp64."""
@@ -313,9 +335,11 @@ def golden_ad2():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["resample", "lj", "fk", "loop", "ad2", "laplacian"]
+    which = sys.argv[1:] or ["resample", "lj", "fk", "loop", "ad2", "laplacian", "schedules"]
     if "laplacian" in which:
         golden_laplacian()
+    if "schedules" in which:
+        golden_schedules()
     if "ad2" in which:
         golden_ad2()
     if "resample" in which:

@@ -1,0 +1,131 @@
+"""Host-side mirrors of the reference interface (pita_b200/*.py) — everything that runs on the host and needs no GPU:
+noise / annealing-factor schedules (folded into kernel arguments as fp64 host scalars), the EGNN parameter container and its
+packed-weight layout, SDETerms, shard bookkeeping, and the rule that the product never computes on the CPU.
+Reference values: tests/golden/schedules.npz and the fk_* fixtures, written by oracle/make_golden.py from the unmodified
+reference.  CPU only."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pita_oracle as O
+
+
+def _g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _cmp(got, ref, what, rtol=1e-12):
+    got = np.asarray(torch.as_tensor(got, dtype=torch.float64))
+    ref = np.asarray(ref, dtype=np.float64)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin), what + ": finiteness differs"
+    err = np.abs(got[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-300)
+    assert err.max() <= rtol, f"{what}: max rel err {err.max():.3e}"
+
+
+def test_noise_schedules_match_reference(golden_dir):
+    """noise_schedules.py:19-28, 64-125 on a grid of 41 times (fp64)."""
+    from pita_b200 import noise_schedules as ns
+    g = _g(golden_dir, "schedules.npz")
+    t = torch.from_numpy(g["t"])
+    cases = {"edm005": ns.ElucidatingNoiseSchedule(0.05, 80, 7), "edm001": ns.ElucidatingNoiseSchedule(0.01, 80, 7),
+             "geo": ns.GeometricNoiseSchedule(0.01, 3.0), "lin": ns.LinearNoiseSchedule(2.5)}
+    for tag, sch in cases.items():
+        _cmp(sch.h(t), g[tag + ".h"], tag + ".h")
+        _cmp(sch.g(t), g[tag + ".g"], tag + ".g")
+        if tag + ".dh_dt" in g.files:
+            _cmp(sch.dh_dt(t), g[tag + ".dh_dt"], tag + ".dh_dt")
+        if tag + ".t_of_h" in g.files:
+            _cmp(sch.t(sch.h(t)), g[tag + ".t_of_h"], tag + ".t(h)", rtol=1e-9)
+    # the oracle's restatement (used by every loop test) against the same reference values
+    for tag, smin in (("edm005", 0.05), ("edm001", 0.01)):
+        o = O.EDMSchedule(smin)
+        _cmp(o.h(t), g[tag + ".h"], "oracle " + tag + ".h")
+        _cmp(o.g(t), g[tag + ".g"], "oracle " + tag + ".g")
+        _cmp(o.dh_dt(t), g[tag + ".dh_dt"], "oracle " + tag + ".dh_dt")
+    # g^2 == dh/dt (what the fused step kernel assumes when it is handed g2 and dh_dt separately)
+    e = cases["edm005"]
+    _cmp(e.g(t) ** 2, np.asarray(e.dh_dt(t)), "g^2 = dh/dt", rtol=1e-12)
+
+
+def test_annealing_factor_schedules_match_reference(golden_dir):
+    """annealing_factor_schedules.py:20-109."""
+    from pita_b200 import annealing_factor_schedules as af
+    g = _g(golden_dir, "schedules.npz")
+    t = torch.from_numpy(g["t"])
+    cases = {"const": (af.ConstantAnnealingFactorSchedule(4.0 / 3.0), O.ConstGamma(4.0 / 3.0)),
+             "linear": (af.LinearAnnealingFactorSchedule(1.5, 1.0, t_start=0.8, t_end=0.2), O.LinearGamma(1.5, 1.0, 0.8, 0.2)),
+             "sigmoid": (af.SigmoidAnnealingFactorSchedule(1.5, 1.0, t_start=0.9, t_end=0.1, sharpness=8.0),
+                         O.SigmoidGamma(1.5, 1.0, 0.9, 0.1, 8.0))}
+    for tag, (mirror, oracle) in cases.items():
+        for obj, who in ((mirror, "pita_b200"), (oracle, "oracle")):
+            _cmp(obj.gamma(t), g[tag + ".gamma"], f"{who} {tag}.gamma")
+            _cmp(obj.dgamma_dt(t), g[tag + ".dgamma_dt"], f"{who} {tag}.dgamma_dt")
+        # python floats are accepted like tensors (the reference wraps them in a float32 torch.tensor, :25-26)
+        assert float(mirror.gamma(0.5)) == pytest.approx(float(g[tag + ".gamma"][20]), rel=1e-6)
+
+
+def test_egnn_container_loads_reference_state_dict_and_packs(golden_dir):
+    """Parameter names / shapes are the reference's, so its checkpoints load; the packed device layout
+    (csrc/egnn_common.cuh::pk) has the size the C ABI reports and is refreshed when a parameter changes in place."""
+    from pita_b200 import _native
+    from pita_b200.egnn_temp_conditioned import EGNN_dynamics, pack_state_dict
+    g = _g(golden_dir, "fk_n13_init.npz")
+    sd = {k[2:]: torch.from_numpy(g[k]).float() for k in g.files if k.startswith("S.")}
+    net = EGNN_dynamics(n_particles=13, n_dimension=3, hidden_nf=32, n_layers=3, act_fn=torch.nn.SiLU(), recurrent=True,
+                        tanh=True, attention=True, condition_time=True, condition_temperature=True, agg="sum")
+    assert set(net.state_dict().keys()) == set(sd.keys())
+    assert all(net.state_dict()[k].shape == v.shape for k, v in sd.items())
+    net.load_state_dict(sd)  # strict
+    assert sum(p.numel() for p in net.parameters()) == 22533  # LJ config
+    pack = pack_state_dict(net.state_dict(), 32, 3, "cpu")
+    assert pack.dtype == torch.float32 and pack.numel() == _native.load().pita_egnn_pack_floats(32, 3)
+    assert torch.equal(pack[:64], sd["egnn.embedding.weight"].T.contiguous().reshape(-1)[:64]) or pack[:96].abs().sum() > 0
+    # deepcopy-able (energytemp_module.py:99) and the pack cache notices in-place updates (EMA swap, optimizer step)
+    twin = copy.deepcopy(net)
+    p0 = net.packed_weights("cpu")
+    assert net.packed_weights("cpu") is p0
+    with torch.no_grad():
+        next(net.parameters()).add_(1.0)
+    assert net.packed_weights("cpu") is not p0
+    assert torch.equal(twin.packed_weights("cpu"), p0)
+    # configurations the native path does not build are refused loudly, not approximated
+    with pytest.raises(NotImplementedError):
+        EGNN_dynamics(n_particles=22, n_dimension=3, hidden_nf=64, n_layers=5, recurrent=True, tanh=True, attention=True,
+                      condition_time=True, condition_temperature=True)
+
+
+def test_sde_terms_container():
+    """SDETerms (sdes.py:34-92): optional fields survive .cpu() and .concatenate()."""
+    from pita_b200.sdes import SDETerms
+    a = SDETerms(drift_X=torch.ones(2, 3), drift_A=torch.zeros(2), divergence_score=torch.arange(2.0))
+    b = SDETerms(drift_X=2 * torch.ones(4, 3), drift_A=torch.ones(4), divergence_score=torch.arange(4.0))
+    c = SDETerms.concatenate([SDETerms.cpu(a), b])
+    assert c.drift_X.shape == (6, 3) and c.drift_A.shape == (6,) and c.divergence_score.shape == (6,)
+    assert c.cross_term is None and c.dUt_dt is None and c.diffusion is None
+    with pytest.raises(ValueError):
+        SDETerms.concatenate([])
+
+
+def test_product_refuses_cpu_tensors():
+    """No CPU fallback anywhere on the path: the public entry points raise on host tensors instead of computing."""
+    from pita_b200.lennardjones_energy import LennardJonesEnergy
+    from pita_b200.sde_integration import WeightedSDEIntegrator
+    from pita_b200.utils import num_unique_from_changes, sample_cat_sys
+    tgt = LennardJonesEnergy(dimensionality=39, n_particles=13)
+    with pytest.raises(Exception):
+        tgt(torch.zeros(4, 39))
+    with pytest.raises(Exception):
+        sample_cat_sys(8, torch.zeros(8))
+    integ = WeightedSDEIntegrator(sde=None, num_integration_steps=2, start_resampling_step=0, end_resampling_step=2)
+    with pytest.raises(RuntimeError):
+        integ.integrate_sde(torch.zeros(4, 39), tgt, None)
+    # len(np.unique(ids)) of a wrapped systematic resample == number of cyclic index changes, 0 changes meaning 1 ancestor
+    assert num_unique_from_changes(0) == 1 and num_unique_from_changes(7) == 7
+    # resampling schedule predicate (sde_integration.py:292): (step+1) % interval == 0 inside [start, end)
+    integ.start_resampling_step, integ.end_resampling_step = 2, 6
+    assert [s for s in range(8) if integ._will_resample(s, 2)] == [3, 5]
+    assert not any(integ._will_resample(s, -1) for s in range(8))
