@@ -83,7 +83,9 @@ def test_egnn_container_loads_reference_state_dict_and_packs(golden_dir):
     assert sum(p.numel() for p in net.parameters()) == 22533  # LJ config
     pack = pack_state_dict(net.state_dict(), 32, 3, "cpu")
     assert pack.dtype == torch.float32 and pack.numel() == _native.load().pita_egnn_pack_floats(32, 3)
-    assert torch.equal(pack[:64], sd["egnn.embedding.weight"].T.contiguous().reshape(-1)[:64]) or pack[:96].abs().sum() > 0
+    # header of the pack = the node embedding as the kernels read it: column 0, column 1 of Linear(2 -> 32), then its bias
+    w, b = sd["egnn.embedding.weight"], sd["egnn.embedding.bias"]
+    assert torch.equal(pack[:32], w[:, 0]) and torch.equal(pack[32:64], w[:, 1]) and torch.equal(pack[64:96], b)
     # deepcopy-able (energytemp_module.py:99) and the pack cache notices in-place updates (EMA swap, optimizer step)
     twin = copy.deepcopy(net)
     p0 = net.packed_weights("cpu")
