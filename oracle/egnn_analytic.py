@@ -191,9 +191,32 @@ def _edge_tangent(w, lay, rng, dp, dq, Dd, dea):
     return dms, dtrans
 
 
-def trace_dxL_dy(sd, tcond, y, beta, n):
+def edge_cache(w, lay):
+    """What the score/divergence kernel keeps per middle-layer edge (csrc/egnn_rows.cu, "layer-1 edge cache"): nothing here
+    depends on the tangent node, so it is computed once per tile.  v = Wc1^T (wc2 * silu'(zc)) turns the coordinate-branch
+    tangent  du = <wc2 * silu'(zc), Wc1 dms>  into the dot product  <v, dms>."""
+    e = lay["e"]
+    return dict(f1=e["f1"], m=e["m"], f2=e["f2"], att=e["s"], th=e["th"], v=(w["wc2"] * e["fc"]) @ w["Wc1"])
+
+
+def _edge_tangent_cached(w, lay, cache, rng, dp, dq, Dd, dea):
+    """_edge_tangent in the form the kernel evaluates it: ONE dense product per tangent row (W2), the coordinate tangent by
+    a dot product with the cached v; returns dms (to be summed over senders BEFORE W3a is applied) and dtrans."""
+    dr2 = 2 * (lay["dlt"] * Dd).sum(-1, keepdim=True)
+    dz1 = cache["f1"] * (dp + dq + w["c1"] * dr2 + w["d1"] * dea)
+    dm = cache["f2"] * (dz1 @ w["W2"].T)
+    ds = cache["att"] * (1 - cache["att"]) * (dm * w["wa"]).sum(-1, keepdim=True)
+    dms = dm * cache["att"] + cache["m"] * ds
+    du = (cache["v"] * dms).sum(-1, keepdim=True)
+    dphi = rng * (1 - cache["th"] ** 2) * du
+    ddhat = Dd * lay["inv"] - lay["dlt"] * ((lay["dlt"] * Dd).sum(-1, keepdim=True) / lay["nrm"] * lay["inv"] ** 2)
+    return dms, ddhat * lay["phi"] + lay["dlt"] * lay["inv"] * dphi
+
+
+def trace_dxL_dy(sd, tcond, y, beta, n, cached: bool = False):
     """tr(d x_L / d y) per sample by forward-mode tangents, one tangent node k at a time, using the
-    sparsity the kernels use (layer 0: edges touching k; last layer: receiver k only)."""
+    sparsity the kernels use (layer 0: edges touching k; last layer: receiver k only).  cached=True evaluates the dense
+    middle layer through the per-edge cache exactly as csrc/egnn_rows.cu does."""
     B = y.shape[0]
     _, st = forward_states(sd, tcond, y, beta, n)
     L, off, rng = st["L"], st["off"], st["rng"]
@@ -221,8 +244,11 @@ def trace_dxL_dy(sd, tcond, y, beta, n):
                 dxk = dx[:, :, k, :] + (dtr * off[:, k:k + 1]).sum(3)[:, :, 0, :]  # [3,B,3]
                 tr = tr + dxk.diagonal(dim1=0, dim2=2).sum(-1)
                 break
-            dms, dtr = _edge_tangent(w, lay, rng, dp, dq, Dd, dea)
-            dagg = (dms * off).sum(3)
+            if cached and 0 < l < L - 1:  # the kernel's form of the dense middle layer(s)
+                dms, dtr = _edge_tangent_cached(w, lay, edge_cache(w, lay), rng, dp, dq, Dd, dea)
+            else:
+                dms, dtr = _edge_tangent(w, lay, rng, dp, dq, Dd, dea)
+            dagg = (dms * off).sum(3)  # summed over the sender slots first, W3a once (linearity)
             dz3 = dh @ w["W3h"].T + dagg @ w["W3a"].T
             dh = dh + (lay["f3"] * dz3) @ w["W4"].T
             dx = dx + (dtr * off).sum(3)

@@ -43,3 +43,24 @@ def test_score_divergence_tangent_pass(n, B):
     s, div = A.score_and_divergence(sd, ht, x, torch.tensor(beta, dtype=torch.float64), n)
     assert _rel(s, s_ref) < 1e-11
     assert _rel(div, div_ref) < 1e-10
+
+
+@pytest.mark.parametrize("n,B", [(13, 2), (7, 3)])
+def test_cached_middle_layer_form_is_the_same_trace(n, B):
+    """The form the score/divergence kernel evaluates (per-edge cache, du as a dot with v = Wc1^T (wc2 * silu'(zc)), sender
+    sum before W3a) is algebraically identical to the plain tangent pass — and both match vmap(jacrev)."""
+    sd = O.random_egnn_state(seed=9 + n, dtype=torch.float64, coord_gain=0.3)
+    y = O.centre(O.md_shaped_coords(B, n, seed=n + 2, dtype=torch.float64) * 1.1, n)
+    tc = torch.linspace(-0.3, 0.4, B, dtype=torch.float64)
+    beta = torch.full((B,), 0.9, dtype=torch.float64)
+    plain = A.trace_dxL_dy(sd, tc, y, beta, n)
+    cached = A.trace_dxL_dy(sd, tc, y, beta, n, cached=True)
+    assert _rel(cached, plain) < 1e-12
+    from torch.func import jacrev, vmap
+
+    def xl(t1, y1, b1):  # x_L = vel + y up to the mean removal, whose trace contribution is -3 (translation invariance)
+        return O.egnn_velocity(sd, t1[None], y1[None], b1[None], n)[0]
+
+    jac = vmap(jacrev(xl, argnums=1))(tc, y, beta)
+    tr_vel = jac.diagonal(dim1=-2, dim2=-1).sum(-1)
+    assert _rel(cached - 3 * n, tr_vel) < 1e-10  # tr d remove_mean(vel)/dy == tr d x_L/dy - 3n
