@@ -255,6 +255,99 @@ def trace_dxL_dy(sd, tcond, y, beta, n, cached: bool = False):
     return tr
 
 
+def trace_dxL_dy_ranked(sd, tcond, y, beta, n):
+    """Same trace for the 3-layer network with the middle layer evaluated through the RANK STRUCTURE of its inputs
+    (DESIGN.md §8 item 1 — the algebra of the next kernel revision, checked here before any CUDA is written):
+
+      after layer 0, for every node i != k the three direction tangents are rank one,  dh1_i[a] = cf_a(i) * omega_i,
+      cf_a(i) = -2 (y_i - y_k)_a,  omega_i = W4 (f3_i * W3a wvec_ik);  so on an edge (i, j) with i != k and j != k
+
+          dms_a = cf_a(i) T(f1 * A omega_i) + cf_a(j) T(f1 * B omega_j) + dr2_a T(f1 * c1),
+
+      where T is the edge's linear tangent map (W2, silu', attention gate).  T(f1 * c1) does not depend on k (it belongs in
+      the edge cache), and cf_a(i) factors out of the sum over senders, so a pass needs TWO dense products per edge and one
+      accumulator for the A-part instead of three products.  Edges with i == k or j == k (own-direction vectors, edge_attr
+      tangent) are evaluated directly, as the kernel will do in its per-k sections."""
+    B = y.shape[0]
+    _, st = forward_states(sd, tcond, y, beta, n)
+    L, off, rng = st["L"], st["off"], st["rng"]
+    assert L == 3
+    H = sd["egnn.embedding.weight"].shape[0]
+    tr = torch.zeros(B, dtype=y.dtype)
+    eye3 = torch.eye(3, dtype=y.dtype)
+    lay0, lay1, lay2 = st["layers"]
+    w0, w1, w2 = lay0["w"], lay1["w"], lay2["w"]
+    e0, e1 = lay0["e"], lay1["e"]
+
+    def tmap(e, w, vec):  # T: R^H -> dms on [.., B, i, j, H]
+        dm = e["f2"] * (vec @ w["W2"].T)
+        ds = e["s"] * (1 - e["s"]) * (dm * w["wa"]).sum(-1, keepdim=True)
+        return dm * e["s"] + e["m"] * ds
+
+    cache1 = edge_cache(w1, lay1)
+    Tc = tmap(e1, w1, e1["f1"] * w1["c1"])          # k-independent, cacheable
+    duc = (cache1["v"] * Tc).sum(-1, keepdim=True)
+    # layer 0: wvec_ij = T0(f1 * (c1 + d1)) for every edge, omega_ij = W4 (f3_i * W3a wvec_ij)
+    wvec = tmap(e0, w0, e0["f1"] * (w0["c1"] + w0["d1"]))                                   # [B,i,j,H]
+    omega = (lay0["f3"][:, :, None, :] * (wvec @ w0["W3a"].T)) @ w0["W4"].T                  # [B,i,j,H]  (j plays k)
+    for k in range(n):
+        # ---- layer 0 exactly as trace_dxL_dy does (kept dense here; it is not the subject of this function)
+        dx = torch.zeros(3, B, n, 3, dtype=y.dtype)
+        dx[:, :, k, :] = eye3[:, None, :]
+        dh = torch.zeros(3, B, n, H, dtype=y.dtype)
+        Dd0 = dx[:, :, :, None, :] - dx[:, :, None, :, :]
+        dea = 2 * (st["d0"] * Dd0).sum(-1, keepdim=True)
+        dms0, dtr0 = _edge_tangent(w0, lay0, rng, (dh @ w0["A"].T)[:, :, :, None, :], (dh @ w0["B"].T)[:, :, None, :, :], Dd0, dea)
+        dh = dh + (lay0["f3"] * ((dms0 * off).sum(3) @ w0["W3a"].T)) @ w0["W4"].T
+        dx = dx + (dtr0 * off).sum(3)
+        # rank-one claim for i != k
+        cf = -2 * st["d0"][:, :, k, :].permute(2, 0, 1)                                     # [3,B,n]  cf_a(i)
+        om = omega[:, :, k, :]                                                              # [B,n,H]  omega_ik
+        notk = torch.ones(n, dtype=torch.bool)
+        notk[k] = False
+        assert torch.allclose(dh[:, :, notk], cf[:, :, notk, None] * om[None, :, notk], rtol=1e-9, atol=1e-12)
+        # ---- layer 1 through the rank structure
+        PA, PB = om @ w1["A"].T, om @ w1["B"].T                                             # [B,n,H]
+        TP = tmap(e1, w1, e1["f1"] * PA[:, :, None, :])                                     # [B,i,j,H]
+        TQ = tmap(e1, w1, e1["f1"] * PB[:, None, :, :])
+        Dd = dx[:, :, :, None, :] - dx[:, :, None, :, :]
+        dr2 = 2 * (lay1["dlt"] * Dd).sum(-1, keepdim=True)                                  # [3,B,i,j,1]
+        generic = (notk[:, None] & notk[None, :]).to(y.dtype)[None, None, :, :, None] * off
+        dms = (cf[:, :, :, None, None] * TP + cf[:, :, None, :, None] * TQ + dr2 * Tc) * generic
+        du = (cf[:, :, :, None, None] * (cache1["v"] * TP).sum(-1, keepdim=True)
+              + cf[:, :, None, :, None] * (cache1["v"] * TQ).sum(-1, keepdim=True) + dr2 * duc) * generic
+        # special edges (i == k or j == k): direct evaluation with the own-direction vectors and the edge_attr tangent
+        dp = (dh @ w1["A"].T)[:, :, :, None, :]
+        dq = (dh @ w1["B"].T)[:, :, None, :, :]
+        dms_s = tmap(e1, w1, e1["f1"] * (dp + dq + w1["c1"] * dr2 + w1["d1"] * dea))
+        du_s = (cache1["v"] * dms_s).sum(-1, keepdim=True)
+        special = (1 - (notk[:, None] & notk[None, :]).to(y.dtype))[None, None, :, :, None] * off
+        dms = dms + dms_s * special
+        du = du + du_s * special
+        dphi = rng * (1 - e1["th"] ** 2) * du
+        ddhat = Dd * lay1["inv"] - lay1["dlt"] * ((lay1["dlt"] * Dd).sum(-1, keepdim=True) / lay1["nrm"] * lay1["inv"] ** 2)
+        dtr1 = ddhat * lay1["phi"] + lay1["dlt"] * lay1["inv"] * dphi
+        # the aggregate in the factored form: cf_a(i) * sum_j T_P  +  sum_j (cf_a(j) T_Q + dr2_a T_c)  (+ special edges)
+        g2 = generic[0, :, :, :, :]
+        dagg = (cf[:, :, :, None] * (TP * g2).sum(2)[None] + ((cf[:, :, None, :, None] * TQ + dr2 * Tc) * generic).sum(3)
+                + (dms_s * special).sum(3))
+        assert torch.allclose(dagg, dms.sum(3), rtol=1e-9, atol=1e-12)
+        dz3 = dh @ w1["W3h"].T + dagg @ w1["W3a"].T
+        dh = dh + (lay1["f3"] * dz3) @ w1["W4"].T
+        dx = dx + (dtr1 * off).sum(3)
+        # ---- layer 2: receiver k only (as trace_dxL_dy)
+        Dd = dx[:, :, :, None, :] - dx[:, :, None, :, :]
+        dp = (dh @ w2["A"].T)[:, :, :, None, :]
+        dq = (dh @ w2["B"].T)[:, :, None, :, :]
+        sub = {kk: (vv[:, k:k + 1] if torch.is_tensor(vv) and vv.dim() == 4 and vv.shape[1] == n and vv.shape[2] == n else vv)
+               for kk, vv in lay2.items() if kk not in ("e", "w")}
+        sub["e"] = {kk: vv[:, k:k + 1] for kk, vv in lay2["e"].items()}
+        _, dtr2 = _edge_tangent(w2, sub, rng, dp[:, :, k:k + 1], dq, Dd[:, :, k:k + 1], dea[:, :, k:k + 1])
+        dxk = dx[:, :, k, :] + (dtr2 * off[:, k:k + 1]).sum(3)[:, :, 0, :]
+        tr = tr + dxk.diagonal(dim1=0, dim2=2).sum(-1)
+    return tr
+
+
 def score_and_divergence(sd, ht, x, beta, n):
     """ScoreNet.forward and tr(d score/dx)  (score_net.py:13-43; utils.py:43-51), autograd-free."""
     B = x.shape[0]

@@ -64,3 +64,15 @@ def test_cached_middle_layer_form_is_the_same_trace(n, B):
     jac = vmap(jacrev(xl, argnums=1))(tc, y, beta)
     tr_vel = jac.diagonal(dim1=-2, dim2=-1).sum(-1)
     assert _rel(cached - 3 * n, tr_vel) < 1e-10  # tr d remove_mean(vel)/dy == tr d x_L/dy - 3n
+
+
+@pytest.mark.parametrize("n,B", [(13, 2), (6, 3)])
+def test_rank_structured_middle_layer(n, B):
+    """the middle layer through the rank structure of its inputs (two dense products per generic edge,
+    the k-independent third one cached, cf_a(i) factored out of the sender sum) gives the same trace; the function itself
+    asserts the rank-one claim and the factored aggregate on the way."""
+    sd = O.random_egnn_state(seed=19 + n, dtype=torch.float64, coord_gain=0.3)
+    y = O.centre(O.md_shaped_coords(B, n, seed=n + 5, dtype=torch.float64) * 1.15, n)
+    tc = torch.linspace(-0.2, 0.5, B, dtype=torch.float64)
+    beta = torch.full((B,), 1.1, dtype=torch.float64)
+    assert _rel(A.trace_dxL_dy_ranked(sd, tc, y, beta, n), A.trace_dxL_dy(sd, tc, y, beta, n)) < 1e-11
