@@ -72,7 +72,9 @@ int pita_egnn_energy(const float *wpack, int hidden, int layers, int n, const fl
  *   PITA_DIV_3XTF32 tcgen05 tensor cores, error-compensated 3xTF32 (fp32-accurate; the default)
  *   PITA_DIV_TF32   tcgen05 tensor cores, plain TF32 for the divergence (looser, stated bound 5e-2 relative on the
  *                   divergence: measured 5e-4 on LJ-13, 3e-2 on LJ-55); the score stays fp32-accurate (3xTF32)
- * The tensor-core modes need `workspace` (device, >= pita_egnn_score_div_workspace_bytes(n, mode) bytes). */
+ * The tensor-core modes need `workspace` (device, >= pita_egnn_score_div_workspace_bytes(n, mode) bytes: 255 MB for
+ * n = 13, 1.08 GB for n = 55 — per-team scratch and the layer-1 edge cache of the divergence passes; independent of B;
+ * its contents are meaningless between calls, so one buffer per stream can be shared by every call). */
 #define PITA_DIV_FP32 0
 #define PITA_DIV_3XTF32 1
 #define PITA_DIV_TF32 2
