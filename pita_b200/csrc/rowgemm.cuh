@@ -22,6 +22,13 @@ namespace pita {
 namespace rg {
 
 constexpr int kRows = 128;  // rows (threads) per team
+// Tangent operand rows (TS path).  false (default): the row is rounded to TF32 once and multiplied with the EXACTLY split
+// weights (hi + lo): 8 MMAs per product.  true: hi + lo parts of the row as well (full 3xTF32, 12 MMAs).  The error of plain
+// TF32 on this network comes from rounding the WEIGHTS (the same rounded matrix hits every edge and direction: a coherent
+// bias, 3e-2 on the LJ-55 divergence), not from rounding the rows (independent per row, averages out over the 3n x (n-1)
+// terms of the trace): measured divergence error 1.2e-5 (LJ-55) / 3.7e-6 (LJ-13) with hi-only rows vs 5.4e-6 / 8e-7 with
+// hi + lo rows (profiles/r1t_err_by_mode.jsonl), 6 % faster.  Primal rows (store_row) always carry hi + lo.
+constexpr bool kTangentLo = false;
 constexpr int kWSlots = 5;  // weight-tile slots shared by the CTA's teams
 constexpr int kNumVec = 10; // per-layer 32-float vectors: c1 d1 b1 b2 wa ba bc1 wc2 b3 b4
 enum Vec { vC1 = 0, vD1 = 1, vB1 = 2, vB2 = 3, vWA = 4, vBA = 5, vBC1 = 6, vWC2 = 7, vB3 = 8, vB4 = 9 };
@@ -161,12 +168,17 @@ struct Team {
   // shared-memory tile.  No STS, no generic->async proxy fence; measured 541 vs 990 cycles per 3xTF32 round trip
   // (profiles/ubench/roundtrip.cu, bit-identical results).  The slots must not be a live accumulator.
   __device__ __forceinline__ void store_row_tmem(int slot_hi, int slot_lo, const float (&v)[32]) const {
-    if (SPLIT) {
+    if (SPLIT && kTangentLo) {
       float h[32], l[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) umma::split_tf32_tangent(v[k], h[k], l[k]);  // (only tangent rows take the TS path)
       umma::tmem_st_32x32(tmem + 32u * slot_hi, h);
       umma::tmem_st_32x32(tmem + 32u * slot_lo, l);
+    } else if (SPLIT) {
+      float h[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) h[k] = umma::round_tf32(v[k]);
+      umma::tmem_st_32x32(tmem + 32u * slot_hi, h);
     } else {
       umma::tmem_st_32x32(tmem + 32u * slot_hi, v);
     }
@@ -178,10 +190,12 @@ struct Team {
     const uint64_t dB = umma::make_desc_sw128_kmajor(wa);
     if (SPLIT) {
       const uint64_t dBl = umma::make_desc_sw128_kmajor(wa + 4096u);
+      if (kTangentLo) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma::mma_tf32_ts(d, al + 8u * k, dB + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma::mma_tf32_ts(d, al + 8u * k, dB + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+      }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma::mma_tf32_ts(d, ah + 8u * k, dBl + 2 * k, idesc, 1u);
+      for (int k = 0; k < 4; ++k) umma::mma_tf32_ts(d, ah + 8u * k, dBl + 2 * k, idesc, (kTangentLo || accumulate || k > 0) ? 1u : 0u);
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma::mma_tf32_ts(d, ah + 8u * k, dB + 2 * k, idesc, 1u);
     } else {
