@@ -131,3 +131,51 @@ def test_product_refuses_cpu_tensors():
     integ.start_resampling_step, integ.end_resampling_step = 2, 6
     assert [s for s in range(8) if integ._will_resample(s, 2)] == [3, 5]
     assert not any(integ._will_resample(s, -1) for s in range(8))
+
+
+def test_generate_samples_call_contract():
+    """energytemp_module.py:237-298: prior scale sqrt(h(t_start) / gamma(t_start)); first pass on all prior samples; with
+    return_logweights a second pass on the first `inference_batch_size` prior samples with resampling switched off by
+    resampling_interval = num_integration_steps + 1; the reference's return tuples.  Host orchestration only — the
+    integrator and the prior are stand-ins that record how they are called."""
+    from functools import partial
+
+    from pita_b200.annealing_factor_schedules import ConstantAnnealingFactorSchedule
+    from pita_b200.noise_schedules import ElucidatingNoiseSchedule
+    from pita_b200.sampling import generate_samples, prior_scale
+
+    calls = []
+
+    class FakeIntegrator:
+        def integrate_sde(self, x1, energy_function, annealing_factor_schedule, inverse_temperature=1.0,
+                          annealing_factor_score=1.0, resampling_interval=None):
+            calls.append(dict(n=x1.shape[0], interval=resampling_interval, beta=inverse_temperature,
+                              gamma=float(annealing_factor_schedule.gamma(0.3)), score=annealing_factor_score, x1=x1))
+            return x1 + 1.0, torch.zeros(5, x1.shape[0]), [x1.shape[0]] * 5, ["terms"], [0.5]
+
+    class FakePrior:
+        def __init__(self, scale, device):
+            self.scale, self.device = scale, device
+
+        def sample(self, n):
+            return torch.arange(n * 6, dtype=torch.float32).reshape(n, 6) * float(self.scale)
+
+    sched = ElucidatingNoiseSchedule(0.05, 80, 7)
+    kw = dict(weighted_sde_integrator=FakeIntegrator(), energy_function="target", num_samples=10, noise_schedule=sched,
+              annealing_factor_schedule=partial(ConstantAnnealingFactorSchedule), partial_prior=FakePrior, t_start=torch.tensor(1.0),
+              device="cpu", inference_batch_size=4, num_integration_steps=100, inverse_temp=0.75, annealing_factor=4.0 / 3.0)
+    out = generate_samples(**kw)
+    assert len(out) == 4 and len(calls) == 1
+    assert calls[0]["n"] == 10 and calls[0]["interval"] is None and calls[0]["beta"] == 0.75
+    assert calls[0]["gamma"] == pytest.approx(4.0 / 3.0) and calls[0]["score"] == pytest.approx(4.0 / 3.0)  # score factor defaults to it
+    scale = float(prior_scale(sched, ConstantAnnealingFactorSchedule(4.0 / 3.0), torch.tensor(1.0)))
+    assert scale == pytest.approx((80.0 ** 2 / (4.0 / 3.0)) ** 0.5, rel=1e-5)  # h(1) = sigma_max^2
+    assert torch.equal(out[0], calls[0]["x1"] + 1.0) and out[1] == [10] * 5 and out[2] == ["terms"] and out[3] == [0.5]
+    calls.clear()
+    out = generate_samples(return_logweights=True, annealing_factor_score=1.1, **kw)
+    assert len(out) == 6 and len(calls) == 2
+    assert calls[0]["n"] == 10 and calls[0]["interval"] is None and calls[0]["score"] == 1.1
+    assert calls[1]["n"] == 4 and calls[1]["interval"] == 101  # no resampling in the log-weight pass
+    assert torch.equal(calls[1]["x1"], calls[0]["x1"][:4])     # the SAME prior samples, first inference_batch_size of them
+    samples, not_resampled, logw, uniq, terms, acc = out
+    assert samples.shape == (10, 6) and not_resampled.shape == (4, 6) and logw.shape == (5, 4) and uniq == [10] * 5
