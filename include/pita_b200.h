@@ -76,11 +76,21 @@ int pita_egnn_energy(const float *wpack, int hidden, int layers, int n, const fl
  *                   divergence: measured 5e-4 on LJ-13, 3e-2 on LJ-55); the score stays fp32-accurate (3xTF32)
  * The tensor-core modes need `workspace` (device, >= pita_egnn_score_div_workspace_bytes(n, mode) bytes: 255 MB for
  * n = 13, 1.08 GB for n = 55 — per-team scratch and the layer-1 edge cache of the divergence passes; independent of B;
- * its contents are meaningless between calls, so one buffer per stream can be shared by every call). */
+ * its contents are meaningless between calls, so one buffer per stream can be shared by every call).
+ *   PITA_DIV_BILINEAR (round 2, the Python default) tcgen05 tensor cores, the trace in its bilinear form: forward-mode
+ *                   tangent through layer 0, reverse-mode cotangent through layer 2, ONE dense product per (middle-layer
+ *                   edge, tangent node) instead of three (oracle/egnn_bilinear.py); primal products 3xTF32, the n^3
+ *                   products plain TF32 (they carry < 1e-3 of the trace; measured divergence error < 1e-5 relative).
+ *                   workspace: 148 x (particles per phase-A CTA) x 2.1 MB (n = 55) / 118 KB (n = 13), 128-byte aligned;
+ *                   smaller workspaces are accepted (>= one particle) and lower the batch per launch pair. */
 #define PITA_DIV_FP32 0
 #define PITA_DIV_3XTF32 1
 #define PITA_DIV_TF32 2
+#define PITA_DIV_BILINEAR 3
 int64_t pita_egnn_score_div_workspace_bytes(int n, int mode);
+/* Introspection for the tests: float offsets of the per-particle workspace of PITA_DIV_BILINEAR (kFloats, oTS, oTR, oOM, oY,
+ * oX1, oP1, oQ1, oOmg, oAOm, oBOm, oGAgg, oDirect, oPartB, kTS, kTR; csrc/egnn_tri.cuh).  Returns the number of entries. */
+int64_t pita_egnn_tri_workspace_layout(int n, int64_t *out, int max_out);
 int pita_egnn_score_div(const float *wpack, int hidden, int layers, int n, const float *ht, const float *x,
                         const float *beta, int64_t B, float *score, float *div, int mode, void *workspace,
                         int64_t workspace_bytes, void *stream);

@@ -17,7 +17,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpita_b200.so")
-SOURCES = ["capi.cu", "lj.cu", "resample.cu", "sde.cu", "egnn.cu", "egnn_rows.cu", "umma_selftest.cu"]
+SOURCES = ["capi.cu", "lj.cu", "resample.cu", "sde.cu", "egnn.cu", "egnn_rows.cu", "egnn_tri_a.cu", "egnn_tri_b.cu",
+           "umma_selftest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -26,13 +27,16 @@ def _sources():
     return [os.path.join(_CSRC, s) for s in SOURCES if os.path.exists(os.path.join(_CSRC, s))]
 
 
+def _headers():
+    hs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith(".cuh")]
+    return hs + [os.path.join(_HERE, "..", "include", "pita_b200.h")]
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = _sources() + [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "umma.cuh"), os.path.join(_CSRC, "egnn_common.cuh"), os.path.join(_CSRC, "rowgemm.cuh"),
-                         os.path.join(_HERE, "..", "include", "pita_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return any(os.path.getmtime(d) > t for d in _sources() + _headers() if os.path.exists(d))
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -44,14 +48,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     build_dir = os.path.join(_HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
+    hdr_time = max(os.path.getmtime(h) for h in _headers())
     for src in _sources():
         obj = os.path.join(build_dir, os.path.basename(src) + ".o")
         objs.append(obj)
-        if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(
-                os.path.getmtime(src), os.path.getmtime(os.path.join(_CSRC, "common.cuh")),
-                os.path.getmtime(os.path.join(_CSRC, "umma.cuh")), os.path.getmtime(os.path.join(_CSRC, "egnn_common.cuh")),
-                os.path.getmtime(os.path.join(_CSRC, "rowgemm.cuh")),
-                os.path.getmtime(os.path.join(_HERE, "..", "include", "pita_b200.h"))):
+        if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
             continue
         cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
         if verbose:
@@ -93,6 +94,7 @@ SIGNATURES = {
     "pita_egnn_forward": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P]),
     "pita_egnn_energy": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "pita_egnn_score_div_workspace_bytes": (_I64, [_I, _I]),
+    "pita_egnn_tri_workspace_layout": (_I64, [_I, ctypes.POINTER(_I64), _I]),
     "pita_egnn_score_div": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P, _I, _P, _I64, _P]),
     "pita_sde_fk_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _I64, _I, ctypes.POINTER(_SdeParams), _P, _P, _P]),
     "pita_fk_quantile_accumulate": (_I, [_P, _P, _I64, _I, _F, _F, _I, _P, _P, _P]),

@@ -677,6 +677,15 @@ int launch_energy_rows(int n, bool split, const float *w, const float *ht, const
 int64_t score_div_rows_workspace_bytes(int n);
 int launch_score_div_rows(int n, bool split, const float *w, const float *ht, const float *x, const float *beta, int64_t B,
                           float *sc, float *dv, float *scratch, int64_t scratch_bytes, cudaStream_t s);
+namespace tri {
+int launch_tri_phase_a(int n, const float *w, const float *ht, const float *x, const float *beta, int64_t b0, int64_t nb,
+                       float *score, float *ws, int want_div, cudaStream_t s);
+int launch_tri_phase_b(int n, const float *w, const float *ht, int64_t b0, int64_t nb, float *ws, float *divergence,
+                       cudaStream_t s);
+int tri_particles_per_cta_a(int n);
+int64_t workspace_floats_per_particle(int n);
+int64_t workspace_layout(int n, int64_t *out, int max_out);
+}  // namespace tri
 }  // namespace pita
 
 using namespace pita;
@@ -712,9 +721,19 @@ extern "C" int pita_egnn_energy(const float *wpack, int hidden, int layers, int 
 }
 
 
+// particles per (phase A, phase B) launch pair of the bilinear engine: one full wave of phase-A CTAs
+static int64_t tri_batch(int n) { return (int64_t)kNumSMs * tri::tri_particles_per_cta_a(n); }
+
 extern "C" int64_t pita_egnn_score_div_workspace_bytes(int n, int mode) {
   if (mode == PITA_DIV_FP32) return 0;
+  if (n != 13 && n != 55) return -1;
+  if (mode == PITA_DIV_BILINEAR) return tri_batch(n) * tri::workspace_floats_per_particle(n) * 4;
   return pita::score_div_rows_workspace_bytes(n);
+}
+
+extern "C" int64_t pita_egnn_tri_workspace_layout(int n, int64_t *out, int max_out) {
+  if (n != 13 && n != 55) return -1;
+  return tri::workspace_layout(n, out, max_out);
 }
 
 extern "C" int pita_egnn_score_div(const float *wpack, int hidden, int layers, int n, const float *ht, const float *x,
@@ -724,8 +743,25 @@ extern "C" int pita_egnn_score_div(const float *wpack, int hidden, int layers, i
   if (rc) return rc;
   if (B == 0) return PITA_OK;
   PITA_REQUIRE(score, PITA_EINVAL, "egnn_score_div: null output");
-  PITA_REQUIRE(mode >= 0 && mode <= 2, PITA_EINVAL, "egnn_score_div: mode must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
+  PITA_REQUIRE(mode >= 0 && mode <= 3, PITA_EINVAL, "egnn_score_div: mode must be 0 (fp32), 1 (3xTF32), 2 (TF32) or 3 (bilinear)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (mode == PITA_DIV_BILINEAR) {
+    if (div == nullptr) return tri::launch_tri_phase_a(n, wpack, ht, x, beta, 0, B, score, nullptr, 0, s);
+    const int64_t per = tri::workspace_floats_per_particle(n) * 4;
+    PITA_REQUIRE(workspace != nullptr && workspace_bytes >= per && (reinterpret_cast<uintptr_t>(workspace) & 127u) == 0, PITA_EINVAL,
+                 "egnn_score_div: the bilinear engine needs a 128-byte aligned workspace of at least %lld bytes", (long long)per);
+    int64_t batch = workspace_bytes / per;
+    if (batch > tri_batch(n)) batch = tri_batch(n);
+    float *ws = static_cast<float *>(workspace);
+    for (int64_t b0 = 0; b0 < B; b0 += batch) {
+      const int64_t nb = (B - b0 < batch) ? (B - b0) : batch;
+      rc = tri::launch_tri_phase_a(n, wpack, ht, x, beta, b0, nb, score, ws, 1, s);
+      if (rc) return rc;
+      rc = tri::launch_tri_phase_b(n, wpack, ht, b0, nb, ws, div, s);
+      if (rc) return rc;
+    }
+    return PITA_OK;
+  }
   if (mode == PITA_DIV_FP32)
     return n == 13 ? launch_score<13, 13, 2>(wpack, ht, x, beta, B, score, div, s)
                    : launch_score<55, 11, 2>(wpack, ht, x, beta, B, score, div, s);

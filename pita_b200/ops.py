@@ -67,14 +67,15 @@ def egnn_energy(wpack, hidden, layers, n, ht, x, beta, need_grad=True, need_dh=T
     return e, g, dh
 
 
-DIV_MODES = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+DIV_MODES = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bilinear": 3}
 _div_ws = {}
 
 
 def default_div_mode() -> str:
-    """PITA_DIV_MODE=fp32|3xtf32|tf32 (default 3xtf32: tensor cores, fp32-accurate)."""
+    """PITA_DIV_MODE=bilinear|3xtf32|tf32|fp32.  Default: bilinear — the round-2 engine (csrc/egnn_tri_*.cu, one dense product
+    per (middle-layer edge, tangent node)); 3xtf32 / tf32 are the round-1 forward-mode kernel, fp32 the CUDA-core one."""
     import os
-    return os.environ.get("PITA_DIV_MODE", "3xtf32").lower()
+    return os.environ.get("PITA_DIV_MODE", "bilinear").lower()
 
 
 def egnn_score_div(wpack, hidden, layers, n, ht, x, beta, need_div=True, mode=None):
