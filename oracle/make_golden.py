@@ -333,9 +333,203 @@ def golden_ad2():
     print("wrote ad2", float(vel.abs().max()))
 
 
+class _RecordDraws:
+    """Records every torch.randn_like / torch.rand_like the reference makes (the post-processing draws its proposal noise and
+    its accept/reject uniforms from the global generator), so that the CUDA path can be fed the same draws."""
+
+    def __enter__(self):
+        self.randn, self.rand = [], []
+        self._rn, self._r = torch.randn_like, torch.rand_like
+
+        def randn_like(x, *a, **k):
+            v = self._rn(x, *a, **k)
+            self.randn.append(v.detach().clone())
+            return v
+
+        def rand_like(x, *a, **k):
+            v = self._r(x, *a, **k)
+            self.rand.append(v.detach().clone())
+            return v
+
+        torch.randn_like, torch.rand_like = randn_like, rand_like
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn_like, torch.rand_like = self._rn, self._r
+
+
+def golden_post():
+    """Post-processing on the target (sde_integration.py:28-45, 353-470): mala_proposal,
+    metropolis_hastings_mala, metropolis_hastings_mala_adaptive and negative_time_descent of the UNMODIFIED reference on
+    LJ-13, fp64, with one non-finite particle (filtered and moved to the end by the reference, :367-400).  All random draws
+    are recorded.  The accept/reject margins |log u - log ratio| are asserted > 1e-3 so that an fp32 evaluation takes the
+    same decisions."""
+    n, N, steps = 13, 40, 6
+    torch.set_default_dtype(torch.float64)
+    try:
+        tgt = LJTarget(n, temperature=1.0)
+        x0 = O.md_shaped_coords(N, n, seed=77).double()
+        x0 = ref.data_utils.remove_mean(x0, n, 3)
+        bad = 5
+        x0[bad, 4] = float("inf")
+        out = {"n": n, "N": N, "steps": steps, "x0": x0.numpy(), "bad_row": bad}
+
+        def mk(**kw):
+            args = dict(sde=None, num_integration_steps=10, start_resampling_step=0, end_resampling_step=10, lightning_module=None,
+                        partial_annealing_factor_schedule=None, num_negative_time_steps=steps, post_mcmc_steps=steps,
+                        dt_negative_time=2e-4)
+            args.update(kw)
+            return ref.integ.WeightedSDEIntegrator(**args)
+
+        xv = torch.cat([x0[:bad], x0[bad + 1:]])
+        torch.manual_seed(31)
+        with _RecordDraws() as d:
+            xp, lqf, lqb = ref.integ.mala_proposal(xv.clone(), tgt, 2e-4)
+        out.update({"prop.x": xv.numpy(), "prop.dt": 2e-4, "prop.noise": d.randn[0].numpy(), "prop.x_prop": xp.numpy(),
+                    "prop.log_q_fwd": lqf.numpy(), "prop.log_q_bwd": lqb.numpy()})
+
+        for tag, adaptive in (("mala", False), ("mala_adaptive", True)):
+            integ = mk()
+            torch.manual_seed(32 + int(adaptive))
+            with _RecordDraws() as d:
+                if adaptive:
+                    xo, rates = integ.metropolis_hastings_mala_adaptive(x0.clone(), tgt, dt_init=2e-4, return_acceptance_rate=True)
+                else:
+                    xo, rates = integ.metropolis_hastings_mala(x0.clone(), tgt, return_acceptance_rate=True)
+            assert len(d.randn) == steps and len(d.rand) == steps
+            out.update({tag + ".x": xo.numpy(), tag + ".rates": np.array(rates), tag + ".noise": torch.stack(d.randn).numpy(),
+                        tag + ".uniform": torch.stack(d.rand).numpy()})
+            # decision margins, recomputed from the recorded draws
+            xc, dt = xv.clone(), 2e-4
+            lp = tgt(xc)
+            margin = 1e9
+            for k in range(steps):
+                _, g = tgt(xc, return_force=True)
+                xpr = xc + 0.5 * dt * g + np.sqrt(dt) * d.randn[k]
+                lpp, gp = tgt(xpr, return_force=True)
+                lqf = -((xpr - (xc + 0.5 * dt * g)) ** 2).sum(1) / (2 * dt)
+                lqb = -((xc - (xpr + 0.5 * dt * gp)) ** 2).sum(1) / (2 * dt)
+                ratio = lpp - lp + lqb - lqf
+                lu = torch.log(d.rand[k])
+                margin = min(margin, float((lu - ratio).abs().min()))
+                acc = (lu < ratio)
+                xc = torch.where(acc[:, None], xpr, xc)
+                lp = torch.where(acc, lpp, lp)
+                xc = ref.data_utils.remove_mean(xc, n, 3)
+                if adaptive:
+                    dt = dt * 1.1 if float(acc.double().mean()) > 0.55 else dt / 1.1
+            assert torch.allclose(xc, xo[:N - 1], rtol=0, atol=1e-12), "restated MALA loop differs from the reference"
+            assert margin > 1e-3, margin
+            print("wrote %s rates %s margin %.3g" % (tag, np.round(rates, 3), margin))
+        # the reference's non-adaptive MALA with return_acceptance_rate=False is a no-op: `acceptance_rate` is unbound at the
+        # print (:386), the NameError is swallowed by the except (:401) before the update lines run
+        integ = mk()
+        torch.manual_seed(40)
+        xo, none = integ.metropolis_hastings_mala(x0.clone(), tgt, return_acceptance_rate=False)
+        out["mala_norate.x"] = xo.numpy()
+        assert none is None
+
+        for tag, lang in (("descent", False), ("langevin", True)):
+            integ = mk(do_langevin=lang)
+            torch.manual_seed(50)
+            with _RecordDraws() as d:
+                xo = integ.negative_time_descent(xv.clone(), tgt)
+            out[tag + ".x"] = xo.numpy()
+            if lang:
+                out[tag + ".noise"] = torch.stack(d.randn).numpy()
+        np.savez_compressed(os.path.join(OUT, "post_n13.npz"), **out)
+        print("wrote post_n13")
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+def golden_fk_variants():
+    """VEReverseSDE.f branches the default fixtures do not reach: pin_energy=True (energy_net.py:41-48: the
+    model energy is mixed with the clamped target energy by (1-t)^3) and precondition_beta=True on both wrappers
+    (energy_net.py:38-39, score_net.py:37-38).  LJ-13, strong coordinate gain, fp64."""
+    n, B, beta = 13, 5, 0.75
+    sched = ref.noise.ElucidatingNoiseSchedule(sigma_min=0.05, sigma_max=80, rho=7)
+    for tag, t, pin, pre in (("pin", 0.12, True, False), ("precond", 0.37, False, True)):
+        net_e, net_s = make_net(n, 12345, True), make_net(n, 54321, True)
+        gen = torch.Generator().manual_seed(4242 + int(pin))
+        x32 = O.md_shaped_coords(B, n, seed=31) * (1.0 + float(sched.h(torch.tensor(t))) ** 0.5 * 0.3)
+        x32 = ref.data_utils.remove_mean(x32 + (0.02 if pin else 0.3) * torch.randn(B, 3 * n, generator=gen), n, 3)
+        out = {"n": n, "t": t, "beta": beta, "x": x32.double().numpy(), "sigma_min": 0.05, "gamma": 4.0 / 3.0, "pin": int(pin),
+               "precondition_beta": int(pre)}
+        out.update(sd_np(net_e, "E."))
+        out.update(sd_np(net_s, "S."))
+        torch.set_default_dtype(torch.float64)
+        try:
+            en = ref.energy_net.EnergyNet(net_e.double(), precondition_beta=pre)
+            sn = ref.score_net.ScoreNet(net_s.double(), precondition_beta=pre)
+            sde = ref.sdes.VEReverseSDE(sched, energy_net=en, score_net=sn, pin_energy=pin, debias_inference=True,
+                                        cdf=lambda h, xx, b_, _f=sn.forward: ref.utils.compute_divergence_exact(_f, h, xx, b_))
+            sde.trainer = FakeTrainer()
+            gs = ref.anneal.ConstantAnnealingFactorSchedule(4.0 / 3.0)
+            tgt = LJTarget(n, temperature=1.0)
+            terms = sde.f(torch.tensor(t), x32.double().clone(), torch.tensor(beta), gs, 1.0, tgt, resampling_interval=1)
+            for k in ("drift_X", "drift_A", "divergence_score", "cross_term", "dUt_dt"):
+                out[k] = getattr(terms, k).detach().numpy()
+            tt = torch.full((B,), t)
+            xr = x32.double().clone().requires_grad_(True)
+            out["U"] = en.forward_energy(sched.h(tt), xr, torch.tensor(beta), pin=pin, energy_function=tgt, t=tt).detach().numpy()
+            out["gradU"] = en.forward(sched.h(tt), xr, torch.tensor(beta), pin=pin, energy_function=tgt, t=tt).detach().numpy()
+            out["target_logp"] = tgt(x32.double()).numpy()
+        finally:
+            torch.set_default_dtype(torch.float32)
+        np.savez_compressed(os.path.join(OUT, f"fk_n13_{tag}.npz"), **out)
+        print("wrote fk_n13_%s drift_A %s U %s" % (tag, out["drift_A"][:3], out["U"][:3]))
+
+
+def golden_loop_linear():
+    """integrate_sde with a LinearAnnealingFactorSchedule (annealing_factor_schedules.py:34-70): gamma'(t) != 0, so the
+    dgamma/dt * U term of the FK drift (sdes.py:227) is exercised end to end; resampling every step, no end resample."""
+    n, N, S, chunk = 13, 16, 24, 8
+    torch.set_default_dtype(torch.float64)
+    try:
+        net_e = make_net(n, 12345, True).double()
+        net_s = make_net(n, 54321, True).double()
+        sched = ref.noise.ElucidatingNoiseSchedule(sigma_min=0.05, sigma_max=80, rho=7)
+        en, sn = ref.energy_net.EnergyNet(net_e), ref.score_net.ScoreNet(net_s)
+        sde = ref.sdes.VEReverseSDE(sched, energy_net=en, score_net=sn, pin_energy=False, debias_inference=True,
+                                    cdf=lambda h, xx, b_, _f=sn.forward: ref.utils.compute_divergence_exact(_f, h, xx, b_))
+        sde.trainer = FakeTrainer()
+        integ = ref.integ.WeightedSDEIntegrator(
+            sde=sde, num_integration_steps=S, start_resampling_step=0, end_resampling_step=S, lightning_module=FakeLM(),
+            partial_annealing_factor_schedule=None, resampling_interval=1, num_negative_time_steps=0, post_mcmc_steps=0,
+            batch_size=chunk, resample_at_end=False, diffusion_scale=1.0)
+        states = []
+        inner = integ.ddp_batched_euler_maruyama_step
+
+        def recording_step(t, x, a, dt, step, **kw):
+            o = inner(t, x, a, dt, step, **kw)
+            states.append((ref.data_utils.remove_mean(o[0], n, 3).detach().clone(), o[1].detach().clone()))
+            return o
+
+        integ.ddp_batched_euler_maruyama_step = recording_step
+        tgt = LJTarget(n, temperature=1.0)
+        torch.manual_seed(2025)
+        gsch = ref.anneal.LinearAnnealingFactorSchedule(1.5, 1.0, t_start=0.9, t_end=0.2)
+        scale = float((sched.h(torch.tensor(1.0)) / float(gsch.gamma(torch.tensor(1.0)))) ** 0.5)
+        x1 = ref.prior.Prior(scale, n_particles=n, spatial_dim=3).sample(N)
+        x1_in = x1.clone()
+        x, logw, uniq, terms, acc = integ.integrate_sde(x1, tgt, gsch, inverse_temperature=torch.tensor(0.75))
+        out = {"n": n, "N": N, "S": S, "chunk": chunk, "seed": 2025, "beta": 0.75, "start": 0, "end": S, "interval": 1,
+               "gamma_args": np.array([1.5, 1.0, 0.9, 0.2]), "x1": x1_in.detach().numpy(), "x_final": x.detach().numpy(),
+               "logweights": logw.detach().numpy(), "num_unique": np.array(uniq), "prior_scale": scale,
+               "x_steps": torch.stack([s_[0] for s_ in states]).numpy().astype(np.float32),
+               "a_steps": torch.stack([s_[1] for s_ in states]).numpy()}
+        out.update(sd_np(net_e, "E."))
+        out.update(sd_np(net_s, "S."))
+        np.savez_compressed(os.path.join(OUT, "loop_n13_linear.npz"), **out)
+        print("wrote loop_linear", uniq)
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["resample", "lj", "fk", "loop", "ad2", "laplacian", "schedules"]
+    which = sys.argv[1:] or ["resample", "lj", "fk", "loop", "ad2", "laplacian", "schedules", "post", "variants", "loop_linear"]
     if "laplacian" in which:
         golden_laplacian()
     if "schedules" in which:
@@ -350,3 +544,9 @@ if __name__ == "__main__":
         golden_egnn_and_fk()
     if "loop" in which:
         golden_loop()
+    if "post" in which:
+        golden_post()
+    if "variants" in which:
+        golden_fk_variants()
+    if "loop_linear" in which:
+        golden_loop_linear()

@@ -378,12 +378,9 @@ static int launch_lj_pairs(const float *x, int64_t B, float T, float ef, float o
   using C = LJPairCfg<NA, G, CW>;
   const int64_t blocks = (B + C::CPB - 1) / C::CPB;
   PITA_REQUIRE(blocks < (1ll << 31), PITA_EINVAL, "lj: batch too large");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(lj_pairs_kernel<NA, G, CW, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    cudaFuncSetAttribute(lj_pairs_kernel<NA, G, CW, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    attr_set = true;
-  }
+  // per launch: the attribute is per device, and one process may drive several
+  cudaFuncSetAttribute(lj_pairs_kernel<NA, G, CW, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  cudaFuncSetAttribute(lj_pairs_kernel<NA, G, CW, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   if (force != nullptr)
     lj_pairs_kernel<NA, G, CW, true, MINB><<<(unsigned)blocks, C::kThreads, C::kSmemBytes, st>>>(x, B, 1.0f / T, ef, osc, logp, force);
   else

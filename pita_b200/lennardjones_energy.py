@@ -58,7 +58,7 @@ class LennardJonesEnergy:
         logp, force = ops.lj_energy_force(samples, self.n_particles, self.temperature, self.energy_factor, 1.0,
                                           need_force=return_force)
         if return_force:
-            if self.should_normalize:  # chain rule of the unnormalisation the reference differentiates through
-                force = force * self.data_normalization_factor
+            # reference :214-223: `samples` is rebound to the UNNORMALISED coordinates before autograd.grad, so the force is the
+            # gradient w.r.t. those — no data_normalization_factor applied
             return logp, force
         return logp

@@ -11,7 +11,24 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
+import functools
+
 from . import _native as N
+
+
+def _on_device(fn):
+    """Run the native call with the CUDA runtime's current device set to the device of the first tensor argument: the
+    launchers use the runtime's current device, torch's current stream is looked up per tensor device."""
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = next((a.device for a in list(args) + list(kwargs.values()) if torch.is_tensor(a) and a.is_cuda), None)
+        if dev is None:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
 
 
 def _expand(v, B: int, device) -> torch.Tensor:
@@ -27,6 +44,7 @@ def _expand(v, B: int, device) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def lj_energy_force(x: torch.Tensor, n: int, temperature: float = 1.0, energy_factor: float = 1.0,
                     oscillator_scale: float = 1.0, need_force: bool = True):
     lib = N.load()
@@ -43,6 +61,7 @@ def egnn_pack_floats(hidden: int, layers: int) -> int:
     return int(N.load().pita_egnn_pack_floats(hidden, layers))
 
 
+@_on_device
 def egnn_forward(wpack, hidden, layers, n, tcond, y, beta) -> torch.Tensor:
     lib = N.load()
     y = N.as_f32(y)
@@ -54,6 +73,7 @@ def egnn_forward(wpack, hidden, layers, n, tcond, y, beta) -> torch.Tensor:
     return vel
 
 
+@_on_device
 def egnn_energy(wpack, hidden, layers, n, ht, x, beta, need_grad=True, need_dh=True):
     lib = N.load()
     x = N.as_f32(x)
@@ -78,6 +98,7 @@ def default_div_mode() -> str:
     return os.environ.get("PITA_DIV_MODE", "bilinear").lower()
 
 
+@_on_device
 def egnn_score_div(wpack, hidden, layers, n, ht, x, beta, need_div=True, mode=None):
     lib = N.load()
     x = N.as_f32(x)
@@ -101,6 +122,7 @@ def egnn_score_div(wpack, hidden, layers, n, ht, x, beta, need_div=True, mode=No
 
 
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def sde_fk_step(x, grad_u, score, noise, div, dE_dh, energy, n: int, *, g2, gamma, dgamma_dt, dh_dt, dt, sqrt_dt,
                 noise_scale, debias=True, freeze_x=False, remove_mean=True, seed=0, offset=0, want_a_raw=True,
                 out: Optional[torch.Tensor] = None):
@@ -117,10 +139,28 @@ def sde_fk_step(x, grad_u, score, noise, div, dE_dh, energy, n: int, *, g2, gamm
     return x_out, a_raw
 
 
+K_QUANTILE_MAX_CHUNK = 8192  # one CTA sorts a chunk in shared memory (csrc/sde.cu::fk_quantile_kernel)
+
+
+@_on_device
 def fk_quantile_accumulate(a_raw, a, chunk: int, q: float, dt: float, zero_a: bool, want_drift=False):
     lib = N.load()
     a_raw = N.as_f32(a_raw)
     B = a_raw.shape[0]
+    if min(int(chunk), B) > K_QUANTILE_MAX_CHUNK:
+        # inference_batch_size above the in-SMEM sort (e.g. the reference's default batch_size=None: one quantile over the
+        # whole shard, sde_integration.py:312-343 + sdes.py:230): the SAME chunk partition, each chunk's quantile by
+        # torch.quantile on the device (the reference's own op; <= 16M elements per chunk, torch's limit)
+        pieces = []
+        for lo in range(0, B, int(chunk)):
+            c = a_raw[lo:lo + int(chunk)]
+            pieces.append(torch.clamp(c, max=torch.quantile(c, q)))
+        drift = torch.cat(pieces)
+        if zero_a:
+            a_out = torch.zeros_like(a_raw)
+        else:
+            a_out = drift if a is None else a + drift * dt  # a is None: the clamped values themselves (include/pita_b200.h)
+        return a_out, (drift if want_drift else None)
     a_out = torch.empty_like(a_raw)
     drift = torch.empty_like(a_raw) if want_drift else None
     N.check(lib.pita_fk_quantile_accumulate(N.ptr(a_raw), N.ptr(a), B, int(chunk), q, dt, int(zero_a), N.ptr(a_out),
@@ -142,6 +182,7 @@ def _workspace(Ntot: int, device) -> torch.Tensor:
     return ws
 
 
+@_on_device
 def softmax_clip(logits: torch.Tensor) -> torch.Tensor:
     lib = N.load()
     logits = N.as_f32(logits)
@@ -152,6 +193,7 @@ def softmax_clip(logits: torch.Tensor) -> torch.Tensor:
     return w
 
 
+@_on_device
 def resample_systematic(w: torch.Tensor, u0: float, slot_lo: int = 0, slot_hi: Optional[int] = None,
                         count_changes: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     lib = N.load()
@@ -167,6 +209,7 @@ def resample_systematic(w: torch.Tensor, u0: float, slot_lo: int = 0, slot_hi: O
     return ids, ch
 
 
+@_on_device
 def gather_rows(src_ptrs: Sequence[int], rows_per_rank: int, ids: torch.Tensor, row_floats: int,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dst[i] = src_{ids[i] // rows_per_rank}[ids[i] % rows_per_rank]; src_ptrs are raw device pointers (peers allowed)."""
@@ -179,6 +222,7 @@ def gather_rows(src_ptrs: Sequence[int], rows_per_rank: int, ids: torch.Tensor, 
     return dst
 
 
+@_on_device
 def remove_mean(x: torch.Tensor, n: int) -> torch.Tensor:
     lib = N.load()
     xc = N.as_f32(x).reshape(-1, 3 * n)
@@ -188,6 +232,7 @@ def remove_mean(x: torch.Tensor, n: int) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def descent_step(x, force, noise, n: int, dt: float, remove_mean_: bool):
     lib = N.load()
     x = N.as_f32(x)
@@ -197,6 +242,7 @@ def descent_step(x, force, noise, n: int, dt: float, remove_mean_: bool):
     return out
 
 
+@_on_device
 def mala_propose(x, force, noise, n: int, dt: float):
     lib = N.load()
     x = N.as_f32(x)
@@ -207,6 +253,7 @@ def mala_propose(x, force, noise, n: int, dt: float):
     return xp, lq
 
 
+@_on_device
 def mala_accept(x, logp, x_prop, logp_prop, force_prop, log_q_fwd, uniform, n: int, dt: float, remove_mean_: bool):
     """In place on x and logp; returns the accepted mask (float 0/1)."""
     lib = N.load()

@@ -87,7 +87,12 @@ class WeightedSDEIntegrator:
         # hooks used by the parity tests to inject the reference's random draws
         self.noise_fn: Optional[Callable[[int, torch.Tensor], torch.Tensor]] = None
         self.u0_fn: Optional[Callable[[int], float]] = None
+        self.mcmc_noise_fn: Optional[Callable[[int, torch.Tensor], torch.Tensor]] = None    # MALA proposal noise of step k
+        self.mcmc_uniform_fn: Optional[Callable[[int, torch.Tensor], torch.Tensor]] = None  # MALA accept/reject uniforms
+        self.descent_noise_fn: Optional[Callable[[int, torch.Tensor], torch.Tensor]] = None  # Langevin noise of descent step k
         self._resampler = None
+        self._resampler_key = None
+        self._noise_call_seed = 0
         self._u0_gen = None
 
     # ------------------------------------------------------------------------------------------
@@ -108,7 +113,13 @@ class WeightedSDEIntegrator:
         The reference lets every rank draw u0 from its own CPU generator and relies on `seed_everything` having made
         them identical (utils.py:112).  With one rank the global CPU generator is used exactly like
         that; with several, rank 0 draws one seed from it and broadcasts it, so ranks cannot disagree on u0."""
-        self._resampler = ShardedResampler(n_local, row_floats, device, group=self.process_group, exchange=self.exchange)
+        key = (n_local, row_floats, str(device), id(self.process_group), self.exchange)
+        if self._resampler is None or self._resampler_key != key:  # symmetric-memory buffers are rendezvoused once, then reused
+            self._resampler = ShardedResampler(n_local, row_floats, device, group=self.process_group, exchange=self.exchange)
+            self._resampler_key = key
+        # in-kernel Philox noise: a fresh key per integrate_sde call (drawn from torch's CPU generator, like the reference's
+        # torch.randn stream advances from call to call), so two passes / epochs never reuse the same Brownian increments
+        self._noise_call_seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)) if self.fused_noise else 0
         self._u0_gen = None
         if self._resampler.world > 1:
             import torch.distributed as dist
@@ -254,10 +265,10 @@ class WeightedSDEIntegrator:
         x_next, a_raw = ops.sde_fk_step(x, grad_u, score, noise, div, dE_dh, U, n, g2=sc["g2"], gamma=sc["gamma"],
                                         dgamma_dt=sc["dgamma"], dh_dt=dh_dt, dt=dt, sqrt_dt=sqrt_dt,
                                         noise_scale=self.diffusion_scale * sc["g"], debias=debias, freeze_x=False,
-                                        remove_mean=self.should_mean_free, seed=self.noise_seed,
+                                        remove_mean=self.should_mean_free, seed=self.noise_seed ^ self._noise_call_seed,
                                         offset=step * 65536 + self._world()[1], want_a_raw=debias, out=out)
         if debias:
-            a_next, drift_a = ops.fk_quantile_accumulate(a_raw, a, min(self.batch_size, 8192), 0.9, dt, zero_a,
+            a_next, drift_a = ops.fk_quantile_accumulate(a_raw, a, self.batch_size, 0.9, dt, zero_a,
                                                          want_drift=self.record_sde_terms)
         else:
             a_next, drift_a = torch.zeros_like(a), torch.zeros_like(a)
@@ -280,9 +291,11 @@ class WeightedSDEIntegrator:
     # post-processing on the target (reference :353-470)
     def negative_time_descent(self, x, energy_function):
         n = energy_function.n_particles
-        for _ in range(self.num_negative_time_steps):
+        for k in range(self.num_negative_time_steps):
             _, drift = energy_function(x, return_force=True)
-            noise = torch.randn_like(x) if self.do_langevin else None
+            noise = None
+            if self.do_langevin:
+                noise = self.descent_noise_fn(k, x) if self.descent_noise_fn else torch.randn_like(x)
             x = ops.descent_step(x, drift, noise, n, float(self.dt_negative_time), self.should_mean_free)
         return x
 
@@ -294,14 +307,21 @@ class WeightedSDEIntegrator:
         x_valid, x_invalid = x_curr[valid].contiguous(), x_curr[~valid]
         logp_valid = logp_curr[valid].contiguous()
         rates = []
-        for _ in range(self.post_mcmc_steps):
+        if not adaptive and not return_acceptance_rate:
+            # Reference parity (:386, :401): without return_acceptance_rate the non-adaptive loop prints an unbound
+            # `acceptance_rate`, the NameError is swallowed by its try/except before the update lines run, and the particles
+            # come back unchanged (valid rows first).  integrate_sde always asks for the rates (:203-207).
+            return torch.cat([x_valid, x_invalid], dim=0), None
+        for k in range(self.post_mcmc_steps):
             if x_valid.shape[0] == 0:
                 continue
             _, grad = energy_function(x_valid, return_force=True)
-            x_prop, log_q_fwd = ops.mala_propose(x_valid, grad, torch.randn_like(x_valid), n, float(dt))
+            xi = self.mcmc_noise_fn(k, x_valid) if self.mcmc_noise_fn else torch.randn_like(x_valid)
+            x_prop, log_q_fwd = ops.mala_propose(x_valid, grad, xi, n, float(dt))
             logp_prop, grad_prop = energy_function(x_prop, return_force=True)
+            uni = self.mcmc_uniform_fn(k, logp_valid) if self.mcmc_uniform_fn else torch.rand_like(logp_valid)
             acc = ops.mala_accept(x_valid, logp_valid, x_prop, logp_prop, grad_prop, log_q_fwd,
-                                  torch.rand_like(logp_valid), n, float(dt),
+                                  uni, n, float(dt),
                                   bool(energy_function.is_molecule and self.should_mean_free) if not adaptive
                                   else bool(energy_function.is_molecule))
             rate = acc.mean().item()

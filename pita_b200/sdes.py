@@ -95,8 +95,7 @@ class VEReverseSDE:
         inner = (-nabla_U * bt).sum(-1)
         raw = gamma * gamma * inner + gamma * div_bt + gamma * dU_dt + gamma_energy_schedule.dgamma_dt(t).to(dev) * U
         # clamp at this call's own 0.9-quantile (sdes.py:230) — one chunk == one call
-        drift_A, _ = ops.fk_quantile_accumulate(raw, None, B, 0.9, 0.0, False) if B <= 8192 else (
-            torch.clamp(raw, max=torch.quantile(raw, 0.9)), None)
+        drift_A, _ = ops.fk_quantile_accumulate(raw, None, B, 0.9, 0.0, False)
         return SDETerms(drift_X=drift_X, drift_A=drift_A, divergence_score=div_bt, cross_term=inner, dUt_dt=dU_dt)
 
     def diffusion(self, t, x, diffusion_scale):

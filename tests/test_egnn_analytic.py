@@ -76,3 +76,44 @@ def test_rank_structured_middle_layer(n, B):
     tc = torch.linspace(-0.2, 0.5, B, dtype=torch.float64)
     beta = torch.full((B,), 1.1, dtype=torch.float64)
     assert _rel(A.trace_dxL_dy_ranked(sd, tc, y, beta, n), A.trace_dxL_dy(sd, tc, y, beta, n)) < 1e-11
+
+
+@pytest.mark.parametrize("n,B", [(13, 2), (5, 3)])
+def test_bilinear_form_of_the_trace(n, B):
+    """oracle/egnn_bilinear.py (the algebra of csrc/egnn_tri_*.cu): forward-mode tangent through layer 0, reverse-mode
+    cotangent through layer 2, bilinear pairing on the middle layer's edges — first with unified per-k node tables, then in
+    the kernel's shape (per-pair tables, generic / S / R items, one dense product per (edge, k)).  Both equal the tangent
+    form, which test_cached_middle_layer_form_is_the_same_trace ties to vmap(jacrev)."""
+    import egnn_bilinear as BL
+    sd = O.random_egnn_state(seed=29 + n, dtype=torch.float64, coord_gain=0.3)
+    y = O.centre(O.md_shaped_coords(B, n, seed=n + 7, dtype=torch.float64) * 1.15, n)
+    tc = torch.linspace(-0.2, 0.5, B, dtype=torch.float64)
+    beta = torch.full((B,), 1.1, dtype=torch.float64)
+    ref = A.trace_dxL_dy(sd, tc, y, beta, n)
+    assert _rel(BL.trace_bilinear_dense(sd, tc, y, beta, n), ref) < 1e-11
+    assert _rel(BL.trace_bilinear_kernel_form(sd, tc, y, beta, n), ref) < 1e-11
+    tab = BL.phase_a_tables(sd, tc, y, beta, n)
+    per_recv = BL.phase_b_items(tab, n, per_receiver=True)
+    assert _rel(tab["direct_node"].sum(1) + per_recv.sum(1), ref) < 1e-11
+
+
+def test_bilinear_form_tolerates_tf32_operands():
+    """The n^3 products of the bilinear form carry < 1e-3 of the trace: truncating their operand rows to TF32 (what the
+    tensor core does to phase B's generic items) moves the LJ-55 'strong' fixture's trace by < 1e-5 relative."""
+    import egnn_bilinear as BL
+    from helpers import golden, state_from_golden
+    g = golden("fk_n13_strong.npz")
+    sd = state_from_golden(g, "S.")
+    x = torch.from_numpy(g["x"]).double()[:2]
+    sched = O.EDMSchedule(float(g["sigma_min"]))
+    ht = sched.h(torch.full((2,), float(g["t"]), dtype=torch.float64))
+    beta = torch.full((2,), float(g["beta"]), dtype=torch.float64)
+    y = (1 + ht)[:, None] ** -0.5 * x
+
+    def trunc(z):
+        i = z.float().contiguous().view(torch.int32) & ~0x1FFF
+        return i.view(torch.float32).double()
+
+    exact = BL.trace_bilinear_kernel_form(sd, 0.125 * torch.log(ht), y, beta, 13)
+    rough = BL.trace_bilinear_kernel_form(sd, 0.125 * torch.log(ht), y, beta, 13, rnd=trunc)
+    assert _rel(rough, exact) < 1e-5

@@ -1,11 +1,12 @@
 """Post-processing on the target energy: negative-time descent, MALA proposal and accept/reject
-(reference models/components/sde_integration.py:28-45, 353-470) vs a float64 restatement on the same draws."""
+(reference models/components/sde_integration.py:28-45, 353-470) vs (a) the UNMODIFIED reference's outputs on recorded draws
+(tests/golden/post_n13.npz, oracle/make_golden.py::golden_post) and (b) a float64 restatement on larger batches."""
 import numpy as np
 import pytest
 import torch
 
 import pita_oracle as O
-from helpers import assert_close
+from helpers import assert_close, golden
 
 pytestmark = pytest.mark.gpu
 
@@ -97,3 +98,78 @@ def test_integrator_post_processing(adaptive):
     assert xm.shape == xbad.shape and len(rates) == 8 and all(0.0 <= r <= 1.0 for r in rates)
     assert torch.isnan(xm[-1]).all() and torch.isfinite(xm[:-1]).all()
     assert max(rates) > 0.3  # dt=1e-4 on relaxed LJ-13 configurations accepts most proposals
+
+
+def _integ(**kw):
+    from pita_b200.sde_integration import WeightedSDEIntegrator
+    args = dict(sde=None, num_integration_steps=10, start_resampling_step=0, end_resampling_step=10, num_negative_time_steps=6,
+                post_mcmc_steps=6, dt_negative_time=2e-4)
+    args.update(kw)
+    return WeightedSDEIntegrator(**args)
+
+
+def _target(n=13):
+    from pita_b200.lennardjones_energy import LennardJonesEnergy
+    return LennardJonesEnergy(dimensionality=3 * n, n_particles=n)
+
+
+def test_mala_proposal_vs_reference_golden():
+    """mala_proposal (reference :28-45) on the reference's own noise draw."""
+    from pita_b200 import sde_integration as SI
+    g = golden("post_n13.npz")
+    x = torch.from_numpy(g["prop.x"]).float().cuda()
+    noise = torch.from_numpy(g["prop.noise"]).float().cuda()
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: noise  # the drop-in draws its proposal noise with torch.randn_like, like the reference
+    try:
+        xp, lqf, lqb = SI.mala_proposal(x, _target(), float(g["prop.dt"]))
+    finally:
+        torch.randn_like = orig
+    assert_close(xp, g["prop.x_prop"], "x_prop", rtol=1e-5)
+    assert_close(lqf, g["prop.log_q_fwd"], "log q(x'|x)")
+    assert_close(lqb, g["prop.log_q_bwd"], "log q(x|x')")
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_mala_loops_vs_reference_golden(adaptive):
+    """metropolis_hastings_mala / _adaptive (reference :362-470): six steps on the reference's recorded proposal noise and
+    uniforms, one non-finite particle.  Acceptance rates (hence every accept/reject decision count and, in the adaptive
+    loop, the whole step-size trajectory) must match exactly; particles to 1e-4; the invalid row comes back last."""
+    g = golden("post_n13.npz")
+    tag = "mala_adaptive" if adaptive else "mala"
+    integ = _integ(adaptive_mcmc=adaptive)
+    noise = torch.from_numpy(g[tag + ".noise"]).float().cuda()
+    uni = torch.from_numpy(g[tag + ".uniform"]).float().cuda()
+    integ.mcmc_noise_fn = lambda k, x: noise[k]
+    integ.mcmc_uniform_fn = lambda k, lp: uni[k]
+    x0 = torch.from_numpy(g["x0"]).float().cuda()
+    if adaptive:
+        x, rates = integ.metropolis_hastings_mala_adaptive(x0, _target(), dt_init=2e-4, return_acceptance_rate=True)
+    else:
+        x, rates = integ.metropolis_hastings_mala(x0, _target(), return_acceptance_rate=True)
+    np.testing.assert_allclose(np.array(rates), g[tag + ".rates"], rtol=0, atol=1e-7)
+    ref = g[tag + ".x"]
+    assert not np.isfinite(ref[-1]).all() and not torch.isfinite(x[-1]).all(), "the non-finite particle is moved to the end"
+    assert_close(x[:-1], ref[:-1], "particles after MALA")
+
+
+def test_mala_without_rates_is_the_references_noop():
+    """Reference quirk pinned (:386, :401): return_acceptance_rate=False makes the non-adaptive loop a no-op."""
+    g = golden("post_n13.npz")
+    x0 = torch.from_numpy(g["x0"]).float().cuda()
+    x, rates = _integ().metropolis_hastings_mala(x0, _target(), return_acceptance_rate=False)
+    assert rates is None
+    ref = g["mala_norate.x"]
+    assert_close(x[:-1], ref[:-1], "particles", rtol=1e-6)
+    assert not torch.isfinite(x[-1]).all()
+
+
+@pytest.mark.parametrize("langevin", [False, True])
+def test_negative_time_descent_vs_reference_golden(langevin):
+    g = golden("post_n13.npz")
+    integ = _integ(do_langevin=langevin)
+    if langevin:
+        noise = torch.from_numpy(g["langevin.noise"]).float().cuda()
+        integ.descent_noise_fn = lambda k, x: noise[k]
+    x = integ.negative_time_descent(torch.from_numpy(g["prop.x"]).float().cuda(), _target())
+    assert_close(x, g[("langevin" if langevin else "descent") + ".x"], "negative_time_descent")
