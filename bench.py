@@ -1,13 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the annealed Feynman-Kac sampling step (BASELINE.json metric: particle-steps/s).
 
-  python bench.py [--gpus N --steps K --warmup W] [--workload lj13|lj55] [--particles P] [--impl ours|reference]
+  python bench.py [--gpus N --steps K --warmup W] [--workload lj55|lj13] [--particles P] [--scaling weak|strong]
+                  [--total-particles T] [--impl ours|reference] [--materialised-noise]
 
-One "step" = one full debiased FK step over all particles: energy net (U, grad U, dU/dt), score net
-(score + exact divergence), fused Euler-Maruyama/FK update with chunk-quantile clamp, and systematic
-resampling (all-gather of log-weights + scan + search + peer-memory gather when N > 1).
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference path on the
-host cores (the reference is pure Python/PyTorch) on a bounded sample of the same workload.
+One "step" = one full debiased FK step over all particles through the integrator's public step
+(`WeightedSDEIntegrator.sharded_step`, the sharded form of the reference's `ddp_batched_euler_maruyama_step`,
+sde_integration.py:214-351): energy net (U, grad U, dU/dt), score net (score + exact divergence), fused
+Euler-Maruyama / FK update with the chunk-quantile clamp, systematic resampling (all-gather of log-weights + scan +
+search + peer-memory gather when N > 1).  The SDE time advances from step to step like in the production loop.
+Prints ONE JSON line (rank 0):
+  value      device-resident throughput (inputs in HBM), CUDA events, max over ranks;
+  e2e        the same metric through `integrate_sde` on HOST buffers: every call copies its particles from pinned host
+             memory, integrates two steps, and copies particles and log-weights back;
+  roofline   the dominant kernel group (score + exact divergence) against the SURVEY §8(d) algorithmic FLOPs, plus the
+             executed-instruction view (tensor pipe / issue slots from the round's ncu capture, profiles/r2_ncu_summary.json);
+  hbm_kernels   achieved GB/s of the HBM-bound kernels (fused SDE/FK step, softmax+scan+search, gather) at this N;
+  cpu_baseline / torch_gpu_baseline   the oracle port of the reference path on the host cores / eagerly on this GPU.
+`--impl reference` times the CPU oracle port of the reference path on all host cores (the reference is pure
+Python/PyTorch; pinned to it by tests/golden) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -28,18 +39,23 @@ WORKLOADS = {
     # BASELINE.json configs[2]: LJ-55, 256k-4M particles sharded across 1/2/4/8 B200
     "lj55": dict(n=55, particles=1 << 18, chunk=512, sigma_min=0.05, label="LJ-55 annealed FK sampling, 256k particles/GPU (BASELINE configs[2])"),
 }
-# measured by ncu on this kernel (bytes per particle per launch; see profiles/README.md); filled from the round's last capture
-NCU_DRAM_BYTES_PER_PARTICLE = {13: (50.237704e9 + 5.881976e9) / 37888,   # profiles/r1n_ncu_scorediv13.txt (37 888 particles)
-                               55: (496.511952e9 + 13.595801e9) / 4736}   # profiles/r1n_ncu_scorediv55.txt (4 736 particles)
 GAMMA = 4.0 / 3.0  # beta_lower / beta for the 4.0 -> 3.0 rung of the temperature ladder (lj13.yaml:44-50)
 BETA = 0.75
-T_STEP = 0.5       # SDE time at which the timed steps are evaluated
+T_STEP = 0.5       # SDE time of the first timed step (the grid then advances by dt = 1/1000 per step)
+S_TOTAL = 1000     # energytemp.yaml:79 — dt of the production loop
 
 
 def egnn_macs_forward(n, H=32, L=3):
     """MAC per sample of the reference's dense EGNN forward."""
     E = n * (n - 1)
     return L * (E * ((2 * H + 2) * H + H * H + H + H * H + H) + n * (2 * H * H + H * H))
+
+
+def executed_tensor_macs(n):
+    """Dense 32x32 products the bilinear engine actually issues per particle (csrc/egnn_tri_*.cu): phase A 25 per edge
+    (3xTF32 = 3 MMAs each), phase B one TF32 product per (edge, k) plus prologue / S / R items."""
+    E = n * (n - 1)
+    return 1024 * (25 * E * 3 + E * (n + 4 * 2 + 4 * 3))
 
 
 class ClockSampler:
@@ -93,28 +109,41 @@ def build_problem(wl, device, seed=12345):
     return sde, sched
 
 
-def oracle_step_seconds(wl, n_particles, steps, threads):
-    """CPU oracle port of the reference path: one debiased FK step (fk_drift + update + resample) on a bounded sample."""
+def oracle_step_seconds(wl, n_particles, steps, threads, device="cpu", chunk=None):
+    """Oracle port of the reference path (plain torch, vmap(jacrev) divergence like utils.py:30-51): one debiased FK step
+    (fk_drift per inference chunk + update + resample) on a bounded sample; on the host cores or eagerly on a GPU."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import pita_oracle as O
     torch.set_num_threads(threads)
     n = wl["n"]
-    sd = O.random_egnn_state(seed=12345, dtype=torch.float32)
-    sched = O.EDMSchedule(wl["sigma_min"])
-    gen = torch.Generator().manual_seed(0)
-    scale = float((sched.h(torch.tensor(T_STEP)) / GAMMA) ** 0.5)
-    x = O.mean_free_prior(n_particles, n, scale, gen=gen)
-    cfg = O.LoopConfig(n=n, steps=1, chunk=min(wl["chunk"], n_particles), beta=BETA, resampling_interval=1)
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        d = O.fk_drift(sd, sd, sched, O.ConstGamma(GAMMA), T_STEP, x, BETA, n)
-        g = float(sched.g(torch.tensor(T_STEP)))
-        xn = x + d.drift_x * 1e-3 + g * torch.randn_like(x) * np.sqrt(1e-3)
-        ids = O.systematic_resample(d.drift_a * 1e-3, 0.5)
-        x = O.centre(xn[torch.from_numpy(ids)], n).detach()
-        times.append(time.perf_counter() - t0)
+    chunk = chunk or n_particles
+    with torch.device(device):
+        sd = {k: v.to(device) for k, v in O.random_egnn_state(seed=12345, dtype=torch.float32).items()}
+        sched = O.EDMSchedule(wl["sigma_min"])
+        gen = torch.Generator(device="cpu").manual_seed(0)
+        scale = float((sched.h(torch.tensor(T_STEP, device="cpu")) / GAMMA) ** 0.5)
+        with torch.device("cpu"):
+            x = O.mean_free_prior(n_particles, n, scale, gen=gen)
+        x = x.to(device)
+        g = float(sched.g(torch.tensor(T_STEP, device="cpu")))
+        times = []
+        for _ in range(steps):
+            if device != "cpu":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dx, da = [], []
+            for lo in range(0, n_particles, chunk):  # the reference's inference_batch_size loop (sde_integration.py:312-343)
+                d = O.fk_drift(sd, sd, sched, O.ConstGamma(GAMMA), T_STEP, x[lo:lo + chunk], BETA, n)
+                dx.append(d.drift_x)
+                da.append(d.drift_a)
+            drift_x, drift_a = torch.cat(dx), torch.cat(da)
+            xn = x + drift_x * 1e-3 + g * torch.randn_like(x) * np.sqrt(1e-3)
+            ids = O.systematic_resample((drift_a * 1e-3).cpu(), 0.5)
+            x = O.centre(xn[torch.from_numpy(ids).to(device)], n).detach()
+            if device != "cpu":
+                torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
     return times
 
 
@@ -125,18 +154,62 @@ def run_reference(args, wl):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = args.cpu_particles or (64 if wl["n"] == 13 else 4)
-    ts = oracle_step_seconds(wl, sample, args.warmup + args.steps, threads)[args.warmup:]
+    sample = args.cpu_particles or (512 if wl["n"] == 13 else 16)
+    chunk = 64 if wl["n"] == 13 else 8  # larger LJ-55 chunks exhaust host memory; chunks run back to back
+    ts = oracle_step_seconds(wl, sample, args.warmup + args.steps, threads, chunk=chunk)[args.warmup:]
     total = sum(ts)
     val = sample * len(ts) / total
     line = {"impl": "reference", "metric": "particle_steps_per_s", "value": val, "unit": "particle-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["label"], "sample": "%d particles/step on the host" % sample},
+            "config": {"workload": wl["label"], "sample": "%d particles/step on the host, inference chunks of %d" % (sample, chunk)},
             "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-                             "sample": "%d particles x %d steps, torch CPU oracle (vmap(jacrev) divergence)" % (sample, len(ts))},
+                             "sample": "%d particles x %d steps in chunks of %d, torch CPU oracle (vmap(jacrev) divergence)" % (sample, len(ts), chunk)},
             "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def timed(fn, reps, flush):
+    """Median CUDA-event time (ms) of fn() on the current stream, L2 flushed before every launch."""
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+def exchange_check(integ, dev, world, rank, Nl, D):
+    """Driver-visible multi-GPU correctness: rows that encode their own global index go through the sharded resampler
+    (all-gather of a, global scan, peer-memory gather); every rank's result must be the rows its own slots' ancestors
+    name, the ancestors computed independently by a full single-rank pita_resample_systematic over all N weights
+    (bit-exact against the reference's sample_cat_sys in tests/test_gpu_resample.py)."""
+    import torch.distributed as dist
+    from pita_b200 import ops
+    rs = integ._resampler
+    N = Nl * world
+    gen = torch.Generator(device=dev).manual_seed(99)  # same stream on every rank
+    a_full_ref = torch.randn(N, device=dev, generator=gen) * 3.0
+    u0 = 0.3141592653589793
+    lo = rank * Nl
+    x_local = (torch.arange(lo, lo + Nl, device=dev, dtype=torch.float32)[:, None] + torch.zeros(1, D, device=dev)).contiguous()
+    a_g = rs.gather_logweights(a_full_ref[lo:lo + Nl].contiguous())
+    ok = bool(torch.equal(a_g, a_full_ref))
+    buf = rs.particle_buffer()
+    if buf is not None:
+        buf.copy_(x_local)
+        x_local = buf
+    x_new, changes = rs.resample(x_local, a_g, u0)
+    ids_all, ch = ops.resample_systematic(ops.softmax_clip(a_full_ref), u0, 0, N, count_changes=True)
+    ok = ok and bool(torch.equal(x_new[:, 0].long(), ids_all[lo:lo + Nl])) and bool(torch.equal(x_new[:, 0], x_new[:, D - 1]))
+    ok = ok and int(changes.item()) == int(ch.item())
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
 
 
 def main():
@@ -149,9 +222,12 @@ def main():
     # fits one GPU); --workload lj13 runs configs[1] (LJ-13, 2^20 particles)
     ap.add_argument("--workload", default=os.environ.get("PITA_BENCH_WORKLOAD", "lj55"), choices=sorted(WORKLOADS))
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--total-particles", type=int, default=1 << 20, help="--scaling strong: particles over ALL GPUs")
     ap.add_argument("--cpu-particles", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fused-noise", action="store_true", help="in-kernel Philox noise instead of a materialised randn tensor")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--materialised-noise", action="store_true", help="torch.randn noise tensor instead of in-kernel Philox")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.particles:
@@ -172,41 +248,50 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.scaling == "strong":
+        wl["particles"] = args.total_particles // world
+        wl["label"] = "LJ-%d annealed FK sampling, %d particles in total (strong scaling)" % (wl["n"], args.total_particles)
     n, D, Nl = wl["n"], 3 * wl["n"], wl["particles"]
     N = Nl * world
     sde, sched = build_problem(wl, dev)
     K, W = args.steps, args.warmup
-    S_total = 1000  # energytemp.yaml:79 — dt of the production loop
-    integ = WeightedSDEIntegrator(sde=sde, num_integration_steps=S_total, start_resampling_step=0, end_resampling_step=S_total,
+    fused = not args.materialised_noise
+    integ = WeightedSDEIntegrator(sde=sde, num_integration_steps=S_TOTAL, start_resampling_step=0, end_resampling_step=S_TOTAL,
                                   lightning_module=None, resampling_interval=1, num_negative_time_steps=0, post_mcmc_steps=0,
-                                  batch_size=wl["chunk"], fused_noise=args.fused_noise, collect_logweights=False)
+                                  batch_size=wl["chunk"], fused_noise=fused, collect_logweights=False)
     gam = ConstantAnnealingFactorSchedule(GAMMA)
     tgt = LennardJonesEnergy(dimensionality=D, n_particles=n)
     scale = float((sched.h(torch.tensor(T_STEP, dtype=torch.float64)) / GAMMA) ** 0.5)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = ops.remove_mean(torch.randn(Nl, D, device=dev, generator=gen) * scale, n)
     a = torch.zeros(Nl, device=dev)
-    torch.cuda.manual_seed(4321 + rank)  # per-rank diffusion noise
+    torch.manual_seed(777)               # same CPU stream on every rank (Philox key of the call, u0)
+    torch.cuda.manual_seed(4321 + rank)  # per-rank diffusion noise when it is materialised
     integ.prepare(Nl, D, dev)
-    dt, sqrt_dt = 1.0 / S_total, float(torch.tensor(1.0 / S_total).sqrt())
-    step0 = int(round((1.0 - T_STEP) * S_total))
+    dt = 1.0 / S_TOTAL
+    sqrt_dt = float(torch.tensor(dt).sqrt())
+    times = torch.linspace(1.0, 0.0, S_TOTAL + 1)[:-1]
+    step0 = int(round((1.0 - T_STEP) * S_TOTAL))
 
     def fk_step(xx, aa, k):
-        return integ._fk_step(T_STEP, step0 + k, xx, aa, dt, sqrt_dt, BETA, n, gam, tgt, 1)[:2]
+        return integ.sharded_step(float(times[step0 + k]), step0 + k, xx, aa, dt, sqrt_dt, BETA, n, gam, tgt, 1)[:2]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: inputs live in HBM; working set (x, grads, scores, noise) > L2 for the default sizes
+    exchange_parity = None
+    if world > 1:
+        exchange_parity = exchange_check(integ, dev, world, rank, Nl, D)
+
+    # ---- device-resident timing: inputs live in HBM; working set (x, grads, scores) > L2 for the default sizes
     for k in range(W):
         x, a = fk_step(x, a, k)
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kern_ev = []
     ev[0].record()
     for k in range(K):
         x, a = fk_step(x, a, W + k)
@@ -220,19 +305,11 @@ def main():
     ms = float(tmax.item())
     value = N * K / (ms * 1e-3)
 
-    # ---- dominant kernel (score + exact divergence) timed alone on the launching stream, L2 flushed between launches
+    # ---- dominant kernel group (score + exact divergence) timed alone on the launching stream, L2 flushed between launches
     ht = torch.full((Nl,), float(sched.h(torch.tensor(T_STEP, dtype=torch.float64))), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    kt = []
-    for _ in range(3 if n == 13 else 2):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        sde.score_net.score_and_divergence(ht, x, BETA)
-        e1.record()
-        torch.cuda.synchronize()
-        kt.append(e0.elapsed_time(e1))
-    k_ms = sorted(kt)[len(kt) // 2] if len(kt) > 2 else min(kt)
+    k_ms = timed(lambda: sde.score_net.score_and_divergence(ht, x, BETA), 3 if n == 13 else 2, flush)
+    en_ms = timed(lambda: sde.energy_net._terms(ht, x, BETA, True, True), 2, flush)
     alg_flops = (3 * n + 1) * 2.0 * egnn_macs_forward(n) * Nl  # (3n+1) forward-equivalents per particle
     peaks = {}
     try:
@@ -240,78 +317,138 @@ def main():
     except Exception:  # noqa: BLE001
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved_tf = alg_flops / (k_ms * 1e-3) / 1e12
-    # DRAM traffic of this kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum), captured on a smaller
-    # launch of the same kernel and scaled per particle (profiles/README.md names the capture); None if never captured
-    traffic = NCU_DRAM_BYTES_PER_PARTICLE.get(n)
-    roofline = {"kernel": "egnn_score_div_rows_kernel (%s)" % ops.default_div_mode(), "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None if traffic is None else traffic * Nl, "kernel_ms": k_ms,
+    ncu = {}
+    try:  # written from the round's last `ncu --set full` capture by profiles/ncu_to_json.py
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json"))).get("n%d" % n, {})
+    except Exception:  # noqa: BLE001
+        pass
+    traffic = ncu.get("dram_bytes_per_particle")
+    roofline = {"kernel": "score + exact divergence: tri_phase_a_kernel + tri_phase_b_kernel (%s)" % ops.default_div_mode(),
+                "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "traffic": None if traffic is None else traffic * Nl, "kernel_ms": k_ms,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
-                "note": "algorithmic FLOPs = (3n+1) dense EGNN forwards per particle (SURVEY 8d); the kernel executes ~21 (n=13) / ~76 (n=55) "
-                        "forward-equivalents (structured tangents) as tcgen05 kind::tf32 MMAs (x3 in 3xtf32 mode) against the bf16 peak"}
+                "executed_tflops": 2.0 * executed_tensor_macs(n) * Nl / (k_ms * 1e-3) / 1e12,
+                "ncu": ncu or None,
+                "note": "achieved = SURVEY 8d algorithmic FLOPs ((3n+1) dense EGNN forwards per particle) / time: the convention the "
+                        "contract asks for.  The bilinear engine EXECUTES ~%.0fx fewer tensor FLOPs than that (executed_tflops), as "
+                        "tcgen05 kind::tf32 MMAs; in practice it is bound by the CUDA-core issue rate of the element-wise work around "
+                        "every product (ncu: issue-slot and tensor-pipe utilisation), not by the tensor pipe"
+                        % (alg_flops / (2.0 * executed_tensor_macs(n) * Nl))}
+
+    # ---- HBM-bound kernels of the step at this N (algorithmic bytes of SURVEY §8d / achieved GB/s / fraction of the measured peak)
+    gu, sc_ = torch.randn_like(x), torch.randn_like(x)
+    dv, dh, en = (torch.randn(Nl, device=dev) for _ in range(3))
+    sp = dict(g2=2.0, gamma=GAMMA, dgamma_dt=0.0, dh_dt=1.0, dt=dt, sqrt_dt=sqrt_dt, noise_scale=1.4)
+    t_sde = timed(lambda: ops.sde_fk_step(x, gu, sc_, None, dv, dh, en, n, seed=1, offset=3, **sp), 5, flush)
+    araw = torch.randn(Nl, device=dev)
+    t_q = timed(lambda: ops.fk_quantile_accumulate(araw, a, wl["chunk"], 0.9, dt, False), 5, flush)
+    wts = ops.softmax_clip(araw)
+    t_rs = timed(lambda: ops.resample_systematic(ops.softmax_clip(araw), 0.37), 5, flush)
+    ids, _ = ops.resample_systematic(wts, 0.37)
+    t_g = timed(lambda: ops.gather_rows([x.data_ptr()], Nl, ids, D), 5, flush)
+
+    def hb(bytes_per_particle, t):
+        gbs = bytes_per_particle * Nl / (t * 1e-3) / 1e9
+        return {"ms": t, "bytes_per_particle": bytes_per_particle, "gbs": gbs, "frac_hbm_peak": gbs / hbm_peak}
+
+    hbm_kernels = {"peak_gbs": hbm_peak, "sde_fk_step_kernel (in-kernel Philox)": hb(12 * D + 12 + 12, t_sde),
+                   "fk_quantile_kernel": hb(12, t_q), "softmax + scan + search": hb(4 + 4 + 4 + 8, t_rs),
+                   "gather_rows_kernel": hb(8 + 8 * D, t_g)}
 
     # ---- second half of BASELINE.json's metric: the Lennard-Jones energy+force kernel as a fraction of the FP32 FMA peak
     #      (31 FLOP per unordered pair + 15 per atom), timed alone on this rank's particles, L2 flushed
-    lj_t = []
-    for _ in range(5):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.lj_energy_force(x, n)
-        e1.record()
-        torch.cuda.synchronize()
-        lj_t.append(e0.elapsed_time(e1))
-    lj_ms = sorted(lj_t)[2]
+    lj_ms = timed(lambda: ops.lj_energy_force(x, n), 5, flush)
     fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
     lj_tf = (31 * n * (n - 1) // 2 + 15 * n) * Nl / (lj_ms * 1e-3) / 1e12
     lj_kernel = {"kernel": "lj_pairs_kernel", "configs_per_s": Nl / (lj_ms * 1e-3), "ms": lj_ms, "alg_tflops": lj_tf,
-                 "fp32_peak_tflops": fp32_peak, "frac_fp32_peak": lj_tf / fp32_peak,
-                 "alg_gbs": (8 * D + 4) * Nl / (lj_ms * 1e-3) / 1e9}
+                 "fp32_peak_tflops": fp32_peak, "fp32_peak_source": "derived: 148 SMs x 128 lanes x 2 FLOP x sm_max_mhz (not in MEASURED_PEAKS.json)",
+                 "frac_fp32_peak": lj_tf / fp32_peak, "alg_gbs": (8 * D + 4) * Nl / (lj_ms * 1e-3) / 1e9}
 
-    # ---- end to end through the public step with HOST buffers: H2D of (x, a), one FK step, D2H of (x', a')
-    hx = torch.empty(Nl, D, pin_memory=True).copy_(x.cpu())
-    ha = torch.zeros(Nl, pin_memory=True)
-    hx_out, ha_out = torch.empty_like(hx).pin_memory(), torch.empty_like(ha).pin_memory()
+    # ---- exchange step alone (N > 1): all-gather of a + global softmax/scan/search + peer gather + barriers + all-reduce
+    exchange_ms = None
+    if world > 1:
+        def one_exchange():
+            a_g = integ._resampler.gather_logweights(araw)
+            buf = integ._resampler.particle_buffer()
+            if buf is not None:
+                buf.copy_(x)
+            integ._resampler.resample(buf if buf is not None else x, a_g, 0.37)
+        one_exchange()
+        barrier()
+        tx = torch.tensor([timed(one_exchange, 5, flush)], device=dev)
+        dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+        exchange_ms = float(tx.item())
+
+    # ---- end to end through integrate_sde with HOST buffers: every call copies its particles from pinned host memory,
+    #      integrates S_E2E steps (the time grid advances) and copies particles + log-weights back
+    S_E2E = 2
+    integ_e = WeightedSDEIntegrator(sde=sde, num_integration_steps=S_E2E, start_resampling_step=0, end_resampling_step=S_E2E,
+                                    lightning_module=None, resampling_interval=1, num_negative_time_steps=0, post_mcmc_steps=0,
+                                    batch_size=wl["chunk"], fused_noise=fused, time_range=S_E2E * dt)
+    hx = torch.empty(N, D, pin_memory=True).copy_(torch.randn(N, D) * scale)
+    hx_out = torch.empty(N, D).pin_memory()
+    hlw = torch.empty(S_E2E, N).pin_memory()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    KE = max(1, min(K, 3))
+    KE = max(1, min(K, 2))
     e0.record()
     for k in range(KE):
-        dx = hx.to(dev, non_blocking=True)
-        da = ha.to(dev, non_blocking=True)
-        dx, da = fk_step(dx, da, W + K + k)
-        hx_out.copy_(dx, non_blocking=True)
-        ha_out.copy_(da, non_blocking=True)
+        dx = hx.to(dev, non_blocking=True)  # the reference's contract: the full [N, D] set goes in, each rank takes its slice
+        xo, lw, uniq, _, _ = integ_e.integrate_sde(dx, tgt, gam, inverse_temperature=BETA)
+        hx_out.copy_(xo, non_blocking=True)
+        hlw.copy_(lw, non_blocking=True)
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_val = N * KE / (float(e2e_ms.item()) * 1e-3)
-    # our kernels per step (profiles/r1d_launches_lj13.csv): energy, score_div, sde_fk_step, fk_quantile + resampling (softmax
-    # partials / finalize / clip, scan tile sums / offsets / bins, search, change count, gather) = 13; torch's randn / fills not counted
-    launches_per_step = 4 + 9
+    e2e_val = N * KE * S_E2E / (float(e2e_ms.item()) * 1e-3)
+    # our kernels per step: energy, phase A x batches, phase B x batches, finalize x batches, sde_fk_step, fk_quantile, resampling
+    # (softmax partials / finalize / clip, scan tile sums / offsets / bins, search, change count, gather) = 9
+    from pita_b200 import _native as Nn
+    per = Nn.load().pita_egnn_score_div_workspace_bytes(n, 3) // max(1, 148 * (2 * (128 // n)))
+    batches = -(-Nl // (148 * 2 * (128 // n)))
+    launches_per_step = 1 + 3 * batches + 2 + 9
+    del per
 
-    cpu_baseline = None
+    cpu_baseline = gpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample = args.cpu_particles or (64 if n == 13 else 4)
-        ts = oracle_step_seconds(wl, sample, 2, threads)[1:]
+        sample = args.cpu_particles or (512 if n == 13 else 16)
+        chunk = 64 if n == 13 else 8
+        ts = oracle_step_seconds(wl, sample, 2, threads, chunk=chunk)[1:]
         cpu_baseline = {"value": sample * len(ts) / sum(ts), "unit": "particle-steps/s", "cores": threads, "kind": "port",
-                        "sample": "%d particles x %d step (after 1 warm-up), torch CPU oracle of the reference path" % (sample, len(ts))}
+                        "sample": "%d particles x %d step (after 1 warm-up) in chunks of %d, torch CPU oracle of the reference path" % (sample, len(ts), chunk)}
+    if rank == 0 and not args.no_gpu_baseline:
+        try:
+            sample = 4096 if n == 13 else 64
+            chunk = 512 if n == 13 else 16
+            ts = oracle_step_seconds(wl, sample, 3, os.cpu_count() or 1, device=str(dev), chunk=chunk)[1:]
+            gpu_baseline = {"value": sample * len(ts) / sum(ts), "unit": "particle-steps/s", "kind": "oracle port of the reference path, "
+                            "plain torch eager on this B200 (vmap(jacrev) divergence, dense [B,n,n] pair tensors)",
+                            "sample": "%d particles x %d steps (after 1 warm-up) in inference chunks of %d" % (sample, len(ts), chunk)}
+        except Exception as exc:  # noqa: BLE001 — a baseline leg must not take the benchmark down
+            gpu_baseline = {"unavailable": repr(exc)[:200]}
 
     if rank == 0:
         line = {"metric": "particle_steps_per_s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K,
-                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["label"], "particles_per_gpu": Nl, "n_atoms": n, "debias_inference": True,
                            "resampling_interval": 1, "chunk": wl["chunk"], "egnn": "hidden 32, 3 layers, random init seed 12345",
-                           "noise": "in-kernel philox" if args.fused_noise else "materialised torch.randn",
-                           "l2": "inputs (%.0f MB/step working set) larger than L2" % (Nl * D * 4 * 5 / 1e6),
+                           "divergence": ops.default_div_mode(),
+                           "noise": "in-kernel philox" if fused else "materialised torch.randn",
+                           "l2": "inputs (%.0f MB/step working set) larger than L2" % (Nl * D * 4 * 4 / 1e6),
                            "exchange": integ._resampler.exchange},
-                "clocks": clk, "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": Nl * D * 4 + Nl * 4,
-                                       "d2h_bytes_per_step": Nl * D * 4 + Nl * 4},
-                "gpu_launches": launches_per_step * K, "roofline": roofline, "lj_kernel": lj_kernel, "cpu_baseline": cpu_baseline}
+                "clocks": clk,
+                "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": N * D * 4 // S_E2E,
+                        "d2h_bytes_per_step": (N * D * 4 + S_E2E * N * 4) // S_E2E,
+                        "how": "integrate_sde(S=%d) per call: pinned host [N,D] -> device, %d steps, particles + log-weights -> pinned host" % (S_E2E, S_E2E)},
+                "gpu_launches": launches_per_step * K, "roofline": roofline, "energy_kernel_ms": en_ms, "hbm_kernels": hbm_kernels,
+                "lj_kernel": lj_kernel, "exchange_parity": exchange_parity, "exchange_ms": exchange_ms,
+                "cpu_baseline": cpu_baseline, "torch_gpu_baseline": gpu_baseline}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -396,13 +396,16 @@ tri_phase_a_kernel(const float *__restrict__ wpack, const float *__restrict__ ht
         }
         // =========================================================================================== layer 0, sweep 2
         T.ld(sK, va);  // f3^0
+        // the yv row of the next edge is fetched while this edge's two products are in flight (vb is free here: h^1 is
+        // re-read from shared memory after the sweep)
+        if (ok) rg::load_vec_global(wsp + W::oOM + ((size_t)i * NP + sender(0)) * 32, vb);
 #pragma unroll 1
         for (int u = 0; u < NP - 1; ++u) {
           const int j = sender(u);
           float *om = wsp + W::oOM + ((size_t)i * NP + j) * 32;
-          if (ok) rg::load_vec_global(om, row);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) row[k] = ok ? row[k] * va[k] : 0.f;
+          for (int k = 0; k < 32; ++k) row[k] = ok ? vb[k] * va[k] : 0.f;
+          if (ok && u + 1 < NP - 1) rg::load_vec_global(wsp + W::oOM + ((size_t)i * NP + sender(u + 1)) * 32, vb);
           put(T, row);
           T.round_trip_ts([&] { mma3(T, sD0, 4, false); });
           T.ld(sD0, row);  // omega_ij
@@ -504,6 +507,12 @@ tri_phase_a_kernel(const float *__restrict__ wpack, const float *__restrict__ ht
         const int j = sender(u), rj = pp * NP + j;
         const float4 yj = sX[rj];
         const Geo g = rg::edge_geo4(xi, sX[2 * kRows + rj], yi, yj);
+        if (want_div && ok) {  // lines read at the end of this edge (written by row j in layer 0): start them moving now
+          const float *trj = wsp + W::oTR + ((size_t)j * NP + i) * kTR + trM;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(trj));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(trj + 8));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(wsp + W::oOM + ((size_t)j * NP + i) * 32));
+        }
         T.ld(sK, row);
         stage1<true>(row, agg, sQ, rj, vec2, g.r2, g.ea);  // agg = f1 (the aggregate is dead code in the last layer)
         put(T, row);

@@ -20,7 +20,8 @@ namespace tri {
 using namespace rg;
 
 constexpr int kComputeThreads = 256;
-// 8 compute warps (2 teams = warpgroups 0 and 1) + one helper warpgroup (MMA warp, copy warp, two idle warps).  Registers are
+// One helper warpgroup (warps 0..3: MMA issuer, copy producer, two idle warps) + 8 compute warps (2 teams = warpgroups 1 and 2:
+// the scheduler favours the higher warp ids, so the compute warps win the issue slot over a polling helper).  Registers are
 // allocated per warpgroup on sm_100: the helper group hands its share to the compute groups (setmaxnreg).
 constexpr int kThreadsB = 384;
 constexpr int kRegsCompute = 224, kRegsHelper = 56;
@@ -29,11 +30,11 @@ template <int NP>
 struct CfgB;
 template <>
 struct CfgB<55> {
-  static constexpr int RS = 64, RPT = 2, KC = 5;
+  static constexpr int RS = 64, RPT = 2, KC = 3, NST = 3;  // k per chunk, ring stages
 };
 template <>
 struct CfgB<13> {
-  static constexpr int RS = 16, RPT = 8, KC = 7;
+  static constexpr int RS = 16, RPT = 8, KC = 5, NST = 3;
 };
 
 template <int NP>
@@ -47,8 +48,8 @@ struct SmemB {
   static constexpr int kChunk = kTSChunk + kTRChunk;             // floats per ring stage
   static constexpr size_t oW = 0;                                // 4 weight tiles (hi + lo): W2, Wc1, Wc1^T, W2^T of layer 1
   static constexpr size_t oG = oW + 4 * 8192;                    // [2 teams] 128 x 128 B staging of the gamma rows (B operand)
-  static constexpr size_t oCh = oG + 2 * 16384;                  // [2 stages][kChunk]
-  static constexpr size_t oF = oCh + 2 * (size_t)kChunk * 4;
+  static constexpr size_t oCh = oG + 2 * 16384;                  // [NST stages][kChunk]
+  static constexpr size_t oF = oCh + C::NST * (size_t)kChunk * 4;
   static constexpr int fVec = 0;                                 // [kNumVec][32] layer-1 vectors
   static constexpr int fY = fVec + kNumVec * 32;                 // [2 teams][NP] float4
   static constexpr int fRed = fY + 2 * NP * 4;                   // [2 teams][4]
@@ -73,6 +74,19 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
       "bra MW_WAIT;\n\t"
       "MW_DONE:\n\t}\n" ::"r"(addr),
       "r"(parity)
+      : "memory");
+}
+// wait of the helper warps (MMA issuer, copy producer): with a suspend-time hint, so that the polling lane sleeps in hardware
+// instead of taking issue slots from the compute warps of its scheduler (ncu r2c: 129 M polls per launch without it)
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "MS_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra MS_DONE;\n\t"
+      "bra MS_WAIT;\n\t"
+      "MS_DONE:\n\t}\n" ::"r"(addr),
+      "r"(parity), "r"(20000u)
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
@@ -146,6 +160,44 @@ __device__ __forceinline__ void commit_to(uint32_t mbar_addr) {
 }
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+// Shared-memory loads of the hot loops: NOT the `asm volatile` lds4 of common.cuh — volatile asm statements keep their
+// program order, which serialises every load behind the arithmetic that consumes the previous one (33 exposed LDS
+// latencies per item: the r2c/r2d profiles).  A plain asm with the address as its only input can be scheduled freely; the
+// `tok` operand ties it to the barrier wait that made the data visible, so it cannot be hoisted above that wait.
+__device__ __forceinline__ float4 lds4s(const float *p, uint32_t tok) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+0];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p)) + tok));
+  return v;
+}
+
+// packed fp32 pairs (FFMA2 / FMUL2: two channels per issue slot — the element-wise work around every product is what bounds
+// this kernel, not the tensor pipe)
+struct pf2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ pf2 pk(float lo, float hi) {
+  pf2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk(pf2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ pf2 fma2(pf2 a, pf2 b, pf2 c) {
+  pf2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return d;
+}
+__device__ __forceinline__ pf2 mul2(pf2 a, pf2 b) {
+  pf2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ float hsum(pf2 a) {
+  float lo, hi;
+  unpk(a, lo, hi);
+  return lo + hi;
+}
 
 template <int NP>
 __global__ void __launch_bounds__(kThreadsB, 1)
@@ -154,7 +206,8 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
   using S = SmemB<NP>;
   using C = CfgB<NP>;
   using W = WS<NP>;
-  constexpr int RS = C::RS, RPT = C::RPT, KC = C::KC, NSLOT = S::NSLOT, NG = S::NG, NCH = S::NCH;
+  constexpr int RS = C::RS, RPT = C::RPT, KC = C::KC, NST = C::NST, NSLOT = S::NSLOT, NG = S::NG, NCH = S::NCH;
+  static_assert(NST <= 4, "barrier slots");
   constexpr int NIT = NP + 4;
   constexpr int L = 3;
   const float rng = kCoordsRange / (float)L;
@@ -167,7 +220,7 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
   float *fl = reinterpret_cast<float *>(base + S::oF);
   float *sVec = fl + S::fVec;
   uint64_t *bars = reinterpret_cast<uint64_t *>(fl + S::fBar);
-  // barrier indices: 0..3 ops_ready[team][stage], 4..7 d_ready[team][stage], 8..9 full[stage], 10..11 empty[stage]
+  // barrier indices: 0..3 ops_ready[team][stage], 4..7 d_ready[team][stage], 8..8+NST-1 full[stage], 12..12+NST-1 empty[stage]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fl + S::fBar + 32);
   const uint32_t bar0 = umma::smem_u32(bars);
 
@@ -175,8 +228,8 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
   if (tid == 0) {
     for (int k = 0; k < 4; ++k) umma::mbar_init(bars + k, 128);
     for (int k = 4; k < 8; ++k) umma::mbar_init(bars + k, 1);
-    for (int k = 8; k < 10; ++k) umma::mbar_init(bars + k, 1);
-    for (int k = 10; k < 12; ++k) umma::mbar_init(bars + k, kComputeThreads);
+    for (int k = 8; k < 8 + NST; ++k) umma::mbar_init(bars + k, 1);
+    for (int k = 12; k < 12 + NST; ++k) umma::mbar_init(bars + k, kComputeThreads);
     umma::fence_mbar_init();
   }
   const float *W1 = wpack + pk::kHeader + pk::kLayer;
@@ -206,10 +259,12 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
   const uint32_t tmem_base = uniform32(*tmem_slot);
   const uint32_t w_addr = uniform32(umma::smem_u32(wsm));
   const int64_t ntile = nb * NG;
+  uint32_t tok0 = 0;  // opaque zero born after the setup barrier: orders the schedulable loads of the layer vectors (lds4s)
+  asm volatile("" : "+r"(tok0)::"memory");
 
-  if (warp >= 8) {
+  if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsHelper));
-  if (warp == 8) {
+  if (warp == 0) {
     // =================================================================================== MMA issuer (one elected lane)
     if (elect_one()) {
       uint32_t rq = 0;  // both teams post the same request sequence
@@ -219,7 +274,7 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
         for (int step = 0; step < 5 + NIT; ++step, ++rq) {
 #pragma unroll 1
           for (uint32_t team = 0; team < 2; ++team) {
-            mbar_wait_addr(bar0 + 8u * (team * 2u + (rq & 1u)), (rq >> 1) & 1u);
+            mbar_wait_sleepy(bar0 + 8u * (team * 2u + (rq & 1u)), (rq >> 1) & 1u);
             umma::fence_after_thread_sync();
             const uint32_t tc = tmem_base + team * 256u;
             if (step < 4) issue_full(tc, w_addr, step);            // prologue products: W2, Wc1, Wc1^T, W2^T
@@ -231,7 +286,7 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == 1) {
     // =================================================================================== copy producer (one elected lane)
     if (elect_one()) {
       uint32_t gc = 0;
@@ -240,15 +295,16 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
         const int grp = (int)(tile - lp * NG);
         const float *wsp = ws + (size_t)lp * (size_t)W::kFloats;
         for (int ch = 0; ch < NCH; ++ch, ++gc) {
-          const uint32_t b = gc & 1u;
-          mbar_wait_addr(bar0 + 8u * (10 + b), ((gc >> 1) & 1u) ^ 1u);
+          const uint32_t b = gc % NST;
+          mbar_wait_sleepy(bar0 + 8u * (12 + b), ((gc / NST) & 1u) ^ 1u);
           const int k0 = ch * KC, kc = (NP - k0 < KC) ? (NP - k0) : KC;
           int nrecv = NP - grp * NSLOT;
           if (nrecv > NSLOT) nrecv = NSLOT;
           const uint32_t full = bar0 + 8u * (8 + b);
           mbar_expect_tx(full, (uint32_t)(kc * NP * kTS * 4 + nrecv * kc * kTR * 4));
           const uint32_t dst = umma::smem_u32(chb + (size_t)b * S::kChunk);
-          bulk_g2s(dst, wsp + W::oTS + (size_t)k0 * NP * kTS, (uint32_t)(kc * NP * kTS * 4), full);
+          for (int q = 0; q < kc; ++q)  // one bulk copy per k: several smaller copies in flight instead of one long one
+            bulk_g2s(dst + (uint32_t)(q * NP * kTS) * 4u, wsp + W::oTS + (size_t)(k0 + q) * NP * kTS, (uint32_t)(NP * kTS * 4), full);
           for (int s = 0; s < nrecv; ++s)
             bulk_g2s(dst + (uint32_t)(S::kTSChunk + s * KC * kTR) * 4u,
                      wsp + W::oTR + ((size_t)(grp * NSLOT + s) * NP + k0) * kTR, (uint32_t)(kc * kTR * 4), full);
@@ -260,7 +316,7 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
     // =================================================================================== compute teams
-    const int team = warp >> 2, r = tid & 127;
+    const int team = (warp >> 2) - 1, r = tid & 127;  // warps 4..7: team 0, warps 8..11: team 1
     TeamB T;
     T.tmem_col = tmem_base + (uint32_t)team * 256u;
     T.tmem = T.tmem_col + (((uint32_t)((warp & 3) * 32)) << 16);
@@ -429,20 +485,22 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
         if (it < NP) {
           // ======================================================================= generic item, k = it
           const int k = it, ch = k / KC, kk = k - ch * KC;
-          const uint32_t b = (gc + (uint32_t)ch) & 1u;
-          if (kk == 0) mbar_wait_addr(bar0 + 8u * (8 + b), ((gc + (uint32_t)ch) >> 1) & 1u);
+          const uint32_t b = (gc + (uint32_t)ch) % NST;
+          if (kk == 0) mbar_wait_addr(bar0 + 8u * (8 + b), ((gc + (uint32_t)ch) / NST) & 1u);
+          uint32_t tok = 0;  // born after the chunk's full-barrier wait
+          asm volatile("" : "+r"(tok)::"memory");
           const float *cb = chb + (size_t)b * S::kChunk;
           const float *tse = cb + ((size_t)kk * NP + j) * kTS;
           const float *tre = cb + S::kTSChunk + ((size_t)cslot * KC + kk) * kTR;
           // small tables
-          const float4 q0 = lds4(tre + trW);        // w0 w1 w2 alpha_i
-          const float4 q1 = lds4(tre + trGX);       // GX 0..3
-          const float4 q2 = lds4(tre + trGX + 4);   // GX 4..7
-          const float4 q3 = lds4(tre + trGX + 8);   // GX 8, M 0..2
-          const float4 q4 = lds4(tre + trGX + 12);  // M 3..6
-          const float4 q5 = lds4(tre + trGX + 16);  // M 7..8, pad
-          const float4 s0 = lds4(tse + tsM), s1 = lds4(tse + tsM + 4), s2 = lds4(tse + tsM + 8);
-          const float4 yk = sY[k];
+          const float4 q0 = lds4s(tre + trW, tok);        // w0 w1 w2 alpha_i
+          const float4 q1 = lds4s(tre + trGX, tok);       // GX 0..3
+          const float4 q2 = lds4s(tre + trGX + 4, tok);   // GX 4..7
+          const float4 q3 = lds4s(tre + trGX + 8, tok);   // GX 8, M 0..2
+          const float4 q4 = lds4s(tre + trGX + 12, tok);  // M 3..6
+          const float4 q5 = lds4s(tre + trGX + 16, tok);  // M 7..8, pad
+          const float4 s0 = lds4s(tse + tsM, tok), s1 = lds4s(tse + tsM + 4, tok), s2 = lds4s(tse + tsM + 8, tok);
+          const float4 yk = lds4s(reinterpret_cast<const float *>(sY + k), tok0);
           const float GX[9] = {q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x};
           const float Mi[9] = {q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w, q5.x, q5.y};
           const float Mj[9] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x};
@@ -460,18 +518,27 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
           const float al_j = q0.x * cfj[0] + q0.y * cfj[1] + q0.z * cfj[2];
           const float bet = q0.x * gv[0] + q0.y * gv[1] + q0.z * gv[2];
           const float xg = xis[0] * gv[0] + xis[1] * gv[1] + xis[2] * gv[2];
-          float b1 = 0.f, b2 = 0.f;
+          float b1, b2;
+          {
+            const pf2 AI = pk(al_i, al_i), AJ = pk(al_j, al_j), BT = pk(bet, bet);
+            pf2 b1p[2] = {pk(0.f, 0.f), pk(0.f, 0.f)}, b2p[2] = {pk(0.f, 0.f), pk(0.f, 0.f)};  // two chains each: ILP at 2 warps / scheduler
 #pragma unroll
-          for (int k4 = 0; k4 < 8; ++k4) {
-            const float4 pa = lds4(tre + trPA + 4 * k4), pb = lds4(tse + tsPB + 4 * k4), c4 = lds4(sVec + vC1 * 32 + 4 * k4);
-            const float pa_[4] = {pa.x, pa.y, pa.z, pa.w}, pb_[4] = {pb.x, pb.y, pb.z, pb.w}, c_[4] = {c4.x, c4.y, c4.z, c4.w};
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const float4 pa = lds4s(tre + trPA + 4 * k4, tok), pb = lds4s(tse + tsPB + 4 * k4, tok), c4 = lds4s(sVec + vC1 * 32 + 4 * k4, tok0);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = 4 * k4 + e;
-              row[c] = f1[c] * fmaf(al_i, pa_[e], fmaf(al_j, pb_[e], bet * c_[e]));
-              b1 = fmaf(vt[c], pa_[e], b1);
-              b2 = fmaf(vt[c], pb_[e], b2);
+              for (int e = 0; e < 2; ++e) {
+                const int c = 4 * k4 + 2 * e;
+                const pf2 pa2 = e ? pk(pa.z, pa.w) : pk(pa.x, pa.y), pb2 = e ? pk(pb.z, pb.w) : pk(pb.x, pb.y);
+                const pf2 c2 = e ? pk(c4.z, c4.w) : pk(c4.x, c4.y);
+                const pf2 vt2 = pk(vt[c], vt[c + 1]);
+                const pf2 u2 = mul2(pk(f1[c], f1[c + 1]), fma2(AI, pa2, fma2(AJ, pb2, mul2(BT, c2))));
+                unpk(u2, row[c], row[c + 1]);
+                b1p[e] = fma2(vt2, pa2, b1p[e]);
+                b2p[e] = fma2(vt2, pb2, b2p[e]);
+              }
             }
+            b1 = hsum(b1p[0]) + hsum(b1p[1]);
+            b2 = hsum(b2p[0]) + hsum(b2p[1]);
           }
           const float tB = cphi * ((xis[0] * cfi[0] + xis[1] * cfi[1] + xis[2] * cfi[2]) * b1 +
                                    (xis[0] * cfj[0] + xis[1] * cfj[1] + xis[2] * cfj[2]) * b2 + xg * duc);
@@ -564,6 +631,8 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
         if (it > 0) {
           const int ip = it - 1;
           T.wait(rq_prev);
+          uint32_t tokf = 0;
+          asm volatile("" : "+r"(tokf)::"memory");
           float dg = 0.f, dw = 0.f, g1;
           T.ld((rq_prev & 1u) ? cD1 : cD0, row);
           if (ip < NP) {
@@ -579,20 +648,28 @@ tri_phase_b_kernel(const float *__restrict__ wpack, float *__restrict__ ws, int6
                 if (slot == s_lo + ss) g1 = v1;
               }
             }
+            {
+              pf2 dgp[2] = {pk(0.f, 0.f), pk(0.f, 0.f)}, dwp[2] = {pk(0.f, 0.f), pk(0.f, 0.f)};
 #pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) {
-              const float4 c4 = lds4(cot_prev + 4 * k4), w4 = lds4(sVec + vWA * 32 + 4 * k4);
-              const float c_[4] = {c4.x, c4.y, c4.z, c4.w}, w_[4] = {w4.x, w4.y, w4.z, w4.w};
+              for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 c4 = lds4s(cot_prev + 4 * k4, tokf), w4 = lds4s(sVec + vWA * 32 + 4 * k4, tok0);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float t = f2[4 * k4 + e] * row[4 * k4 + e];
-                dg = fmaf(t, c_[e], dg);
-                dw = fmaf(t, w_[e], dw);
+                for (int e = 0; e < 2; ++e) {
+                  const int c = 4 * k4 + 2 * e;
+                  const pf2 t2 = mul2(pk(f2[c], f2[c + 1]), pk(row[c], row[c + 1]));
+                  dgp[e] = fma2(t2, e ? pk(c4.z, c4.w) : pk(c4.x, c4.y), dgp[e]);
+                  dwp[e] = fma2(t2, e ? pk(w4.z, w4.w) : pk(w4.x, w4.y), dwp[e]);
+                }
               }
+              dg = hsum(dgp[0]) + hsum(dgp[1]);
+              dw = hsum(dwp[0]) + hsum(dwp[1]);
             }
             // release the chunk once its last item is finished
             const int chp = ip / KC;
-            if (ip == NP - 1 || ip - chp * KC == KC - 1) mbar_arrive(bar0 + 8u * (10 + ((gc + (uint32_t)chp) & 1u)));
+            if (ip == NP - 1 || ip - chp * KC == KC - 1) {
+              asm volatile("" ::"f"(dg), "f"(dw) : "memory");  // the chunk's last reads are complete before it is handed back
+              mbar_arrive(bar0 + 8u * (12 + ((gc + (uint32_t)chp) % NST)));
+            }
           } else {
             const float *cot = (ip == NP) ? (wsp + W::oTR + ((size_t)i * NP + j) * kTR + trGam)
                                           : (wsp + W::oGAgg + ((size_t)i * 3 + (ip - NP - 1)) * 32);

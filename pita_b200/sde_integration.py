@@ -230,6 +230,13 @@ class WeightedSDEIntegrator:
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.process_group)
         return out
 
+    def sharded_step(self, t32, step, x, a, dt, sqrt_dt, beta, n, schedule, energy_function, resampling_interval):
+        """One Euler-Maruyama + FK step on the rank-local shard: the sharded form of the reference's
+        `ddp_batched_euler_maruyama_step` (:214-351), which takes and returns the FULL particle set on every rank.  Here
+        x [N/W, D] and a [N/W] are this rank's block; only a resampling step communicates.  Returns
+        (x_next, a_next, n_unique or its device counter, SDETerms or None).  `prepare()` must have been called."""
+        return self._fk_step(t32, step, x, a, dt, sqrt_dt, beta, n, schedule, energy_function, resampling_interval)
+
     def _fk_step(self, t32, step, x, a, dt, sqrt_dt, beta, n, schedule, energy_function, resampling_interval):
         """One Euler-Maruyama + FK step on the rank-local shard (reference :214-351)."""
         sc = self._step_scalars(t32, schedule)
@@ -310,8 +317,8 @@ class WeightedSDEIntegrator:
         if not adaptive and not return_acceptance_rate:
             # Reference parity (:386, :401): without return_acceptance_rate the non-adaptive loop prints an unbound
             # `acceptance_rate`, the NameError is swallowed by its try/except before the update lines run, and the particles
-            # come back unchanged (valid rows first).  integrate_sde always asks for the rates (:203-207).
-            return torch.cat([x_valid, x_invalid], dim=0), None
+            # come back unchanged and in their original order.  integrate_sde always asks for the rates (:203-207).
+            return x_curr, None
         for k in range(self.post_mcmc_steps):
             if x_valid.shape[0] == 0:
                 continue

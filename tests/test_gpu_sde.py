@@ -72,7 +72,7 @@ def _build_integrator(n, sdE, sdS, S, chunk, **kw):
                                  num_negative_time_steps=0, post_mcmc_steps=0, **kw)
 
 
-def _replay_reference_stream(g, sdE, sdS):
+def _replay_reference_stream(g, sdE, sdS, gamma_sched=None, resample_at_end=True):
     """Replays the reference's CPU random stream through the oracle (which reproduces the reference trajectory,
     tests/test_oracle_golden.py) and returns the per-step noise / offsets it consumed."""
     n, N, S, chunk = int(g["n"]), int(g["N"]), int(g["S"]), int(g["chunk"])
@@ -80,7 +80,7 @@ def _replay_reference_stream(g, sdE, sdS):
     x1 = O.mean_free_prior(N, n, float(g["prior_scale"]), dtype=torch.float64)
     noises, u0s = {}, {}
     cfg = O.LoopConfig(n=n, steps=S, chunk=chunk, beta=float(g["beta"]), resampling_interval=int(g["interval"]),
-                       start_resampling_step=int(g["start"]), end_resampling_step=int(g["end"]), resample_at_end=True)
+                       start_resampling_step=int(g["start"]), end_resampling_step=int(g["end"]), resample_at_end=resample_at_end)
 
     def noise_fn(step, xc):
         z = torch.randn_like(xc)
@@ -91,7 +91,8 @@ def _replay_reference_stream(g, sdE, sdS):
         u0s[step] = float(torch.rand(size=(1,), dtype=torch.float64))
         return u0s[step]
 
-    x_ref, logw_ref, uniq_ref = O.integrate(sdE, sdS, O.EDMSchedule(0.05), O.ConstGamma(float(g["gamma"])), cfg, x1, noise_fn, u0_fn)
+    gs = gamma_sched if gamma_sched is not None else O.ConstGamma(float(g["gamma"]))
+    x_ref, logw_ref, uniq_ref = O.integrate(sdE, sdS, O.EDMSchedule(0.05), gs, cfg, x1, noise_fn, u0_fn)
     assert list(uniq_ref) == list(g["num_unique"])
     return x1, {k: torch.cat(v) for k, v in noises.items()}, u0s
 
@@ -227,3 +228,113 @@ def test_sample_histograms_match_oracle():
     assert torch.isfinite(xs).all() and min(uniq_s) > N // 8
     assert O.w2_1d(p_s, p_ref) <= 1.0 * p_ref.std(), O.w2_1d(p_s, p_ref) / p_ref.std()
     assert O.w2_1d(e_s, e_ref) <= 1.0 * e_ref.std(), O.w2_1d(e_s, e_ref) / e_ref.std()
+
+
+def test_loop_linear_gamma_vs_reference_golden():
+    """integrate_sde under a LinearAnnealingFactorSchedule (gamma'(t) != 0: the dgamma/dt * U term of the FK drift, sdes.py:227,
+    is live) on the reference's own 24-step trajectory, resampling every step: teacher-forced states to 1e-4, free-running
+    ancestor counts identical."""
+    from pita_b200.annealing_factor_schedules import LinearAnnealingFactorSchedule
+    from pita_b200.lennardjones_energy import LennardJonesEnergy
+    g = golden("loop_n13_linear.npz")
+    n, N, S, chunk = int(g["n"]), int(g["N"]), int(g["S"]), int(g["chunk"])
+    sdE, sdS = state_from_golden(g, "E."), state_from_golden(g, "S.")
+    ga = [float(v) for v in g["gamma_args"]]
+    x1, noises, u0s = _replay_reference_stream(g, sdE, sdS, gamma_sched=O.LinearGamma(ga[0], ga[1], ga[2], ga[3]), resample_at_end=False)
+    gam = LinearAnnealingFactorSchedule(ga[0], ga[1], t_start=ga[2], t_end=ga[3])
+    kw = dict(start_resampling_step=0, end_resampling_step=S, resampling_interval=1, resample_at_end=False)
+    tgt = LennardJonesEnergy(dimensionality=3 * n, n_particles=n, temperature=1.0)
+    integ = _build_integrator(n, sdE, sdS, S, chunk, **kw)
+    integ.noise_fn = lambda step, x: noises[step].float().cuda()
+    integ.u0_fn = lambda step: u0s[step]
+    integ.prepare(N, 3 * n, "cuda")
+    times = torch.linspace(1.0, 0.0, S + 1)[:-1]
+    dt = 1.0 / S
+    xs = np.concatenate([g["x1"][None].astype(np.float32), g["x_steps"]])
+    seen_dgamma = False
+    for step in range(S):
+        seen_dgamma |= float(gam.dgamma_dt(times[step])) != 0.0
+        x_in = torch.from_numpy(xs[step]).cuda()
+        a_in = torch.zeros(N, device="cuda")  # resampling every step: a is reset before every step
+        x_out, a_out, _, _ = integ._fk_step(float(times[step]), step, x_in, a_in, dt, float(np.float32(np.sqrt(dt))),
+                                            float(g["beta"]), n, gam, tgt, 1)
+        assert_close(x_out, xs[step + 1], f"x after step {step} (teacher forced)")
+    assert seen_dgamma
+    integ = _build_integrator(n, sdE, sdS, S, chunk, **kw)
+    integ.noise_fn = lambda step, x: noises[step].float().cuda()
+    integ.u0_fn = lambda step: u0s[step]
+    x, logw, uniq, _, _ = integ.integrate_sde(x1.float().cuda(), tgt, gam, inverse_temperature=float(g["beta"]))
+    assert list(uniq) == list(g["num_unique"]), (uniq, list(g["num_unique"]))
+    assert_close(x, g["x_final"], "x_final vs reference", rtol=2e-3)
+
+
+@pytest.mark.parametrize("tag", ["pin", "precond"])
+def test_sde_f_variants_vs_reference_golden(tag):
+    """VEReverseSDE.f with pin_energy=True (energy_net.py:41-48) and with precondition_beta=True on both wrappers
+    (energy_net.py:38-39, score_net.py:37-38) against the reference's fp64 SDETerms."""
+    from pita_b200.annealing_factor_schedules import ConstantAnnealingFactorSchedule
+    from pita_b200.energy_net import EnergyNet
+    from pita_b200.lennardjones_energy import LennardJonesEnergy
+    from pita_b200.noise_schedules import ElucidatingNoiseSchedule
+    from pita_b200.score_net import ScoreNet
+    from pita_b200.sdes import VEReverseSDE
+    g = golden("fk_n13_%s.npz" % tag)
+    n, t, beta = int(g["n"]), float(g["t"]), float(g["beta"])
+    pin, pre = bool(int(g["pin"])), bool(int(g["precondition_beta"]))
+    sched = ElucidatingNoiseSchedule(float(g["sigma_min"]), 80.0, 7.0)
+    en = EnergyNet(make_net(n, state_from_golden(g, "E.")), precondition_beta=pre)
+    sn = ScoreNet(make_net(n, state_from_golden(g, "S.")), precondition_beta=pre)
+    sde = VEReverseSDE(sched, energy_net=en, score_net=sn, pin_energy=pin)
+    tgt = LennardJonesEnergy(dimensionality=3 * n, n_particles=n, temperature=1.0)
+    x = torch.from_numpy(g["x"]).float().cuda()
+    assert_close(tgt(x), g["target_logp"], "target log-prob")
+    terms = sde.f(torch.tensor(t), x, torch.tensor(beta), ConstantAnnealingFactorSchedule(float(g["gamma"])), 1.0, tgt,
+                  resampling_interval=1)
+    assert_close(terms.drift_X, g["drift_X"], "drift_X")
+    assert_close(terms.divergence_score, g["divergence_score"], "div_b")
+    assert_close(terms.cross_term, g["cross_term"], "cross_term")
+    assert_close(terms.dUt_dt, g["dUt_dt"], "dUt_dt")
+    assert_close(terms.drift_A, g["drift_A"], "drift_A")
+    B = x.shape[0]
+    tt = torch.full((B,), t, device="cuda")
+    ht = torch.full((B,), float(sched.h(torch.tensor(t, dtype=torch.float64))), device="cuda")
+    assert_close(en.forward_energy(ht, x, beta, pin=pin, energy_function=tgt, t=tt), g["U"], "forward_energy")
+    assert_close(en.forward(ht, x, beta, pin=pin, energy_function=tgt, t=tt), g["gradU"], "grad U")
+
+
+def test_quantile_chunks_above_the_smem_sort():
+    """inference_batch_size above 8192 (e.g. the reference's default batch_size=None = the whole shard): same chunk
+    partition as the reference (sde_integration.py:312-343), each chunk clamped at its own torch.quantile (sdes.py:230)."""
+    from pita_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    B = 30000
+    raw = torch.randn(B, generator=gen) * 7
+    a = torch.randn(B, generator=gen)
+    for chunk in (B, 12000):
+        a_out, drift = ops.fk_quantile_accumulate(raw.cuda(), a.cuda(), chunk, 0.9, 0.01, False, want_drift=True)
+        ref = torch.cat([torch.clamp(raw[lo:lo + chunk], max=torch.quantile(raw[lo:lo + chunk], 0.9)) for lo in range(0, B, chunk)])
+        assert_close(drift, ref, "drift_A", rtol=1e-6)
+        assert_close(a_out, a.double() + ref.double() * 0.01, "a_next", rtol=1e-6)
+        only, _ = ops.fk_quantile_accumulate(raw.cuda(), None, chunk, 0.9, 0.0, False)
+        assert_close(only, ref, "clamped values", rtol=1e-6)
+
+
+def test_prior_sample():
+    """Prior / MeanFreePrior.sample (energies/base_prior.py:77-83): shape, centre of mass removed per sample, per-coordinate
+    variance scale^2 (n-1)/n, log_prob == the reference's closed form."""
+    import math
+
+    from pita_b200.base_prior import Prior
+    n, scale, N = 13, 2.5, 20000
+    pr = Prior(scale, n_particles=n, spatial_dim=3, device="cuda")
+    torch.manual_seed(0)
+    x = pr.sample(N)
+    assert x.shape == (N, 3 * n) and x.is_cuda and x.dtype == torch.float32
+    assert x.reshape(N, n, 3).mean(1).abs().max().item() < 1e-5
+    var = x.double().var().item()
+    assert abs(var / (scale ** 2 * (n - 1) / n) - 1.0) < 0.02
+    lp = pr.log_prob(x[:7])
+    ref = -0.5 * (x[:7].double() ** 2).sum(1) / scale ** 2 - 0.5 * (n - 1) * 3 * math.log(2 * math.pi * scale ** 2)
+    assert_close(lp, ref, "log_prob", rtol=1e-5)
+    free = Prior(scale, n_particles=n, spatial_dim=3, device="cuda", should_mean_free=False)
+    assert free.sample(5).shape == (5, 3 * n)
