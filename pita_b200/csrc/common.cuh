@@ -69,6 +69,22 @@ __device__ __forceinline__ float4 lds4(const float *p) {
                : "memory");
   return v;
 }
+// Schedulable 128-bit shared-memory load for tables that are CONSTANT once published (layer vectors, class tables): a plain
+// asm (not volatile, no memory clobber) whose only input is the address, so the compiler may issue it ahead of the arithmetic
+// that consumes the previous one — the volatile lds4 above keeps program order and exposes one shared-memory latency per load.
+// Ordering against the barrier that published the table comes from the POINTER: pass it through opq() after that barrier (the
+// stage helpers do so on entry), which also keeps the loads from being hoisted out of the surrounding loops.
+__device__ __forceinline__ float4 lds4c(const float *p) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))));
+  return v;
+}
+__device__ __forceinline__ const float *opq(const float *p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
 __device__ __forceinline__ void sts4(float *p, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "f"(v.x),
                "f"(v.y), "f"(v.z), "f"(v.w)

@@ -11,11 +11,12 @@ namespace rg {
 template <bool KEEP, bool HAS_Q = true>
 __device__ __forceinline__ void stage1(float (&row)[32], float (&f1)[32], const float *qbase, int qrow, const float *vec, float r2,
                                        float ea) {
+  vec = opq(vec);
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) {
     const float4 q = HAS_Q ? qrow_ld4(qbase, qrow, k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 c = lds4(vec + vC1 * 32 + 4 * k4);
-    const float4 d = lds4(vec + vD1 * 32 + 4 * k4);
+    const float4 c = lds4c(vec + vC1 * 32 + 4 * k4);
+    const float4 d = lds4c(vec + vD1 * 32 + 4 * k4);
     const float qq[4] = {q.x, q.y, q.z, q.w}, cc[4] = {c.x, c.y, c.z, c.w}, dd[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -32,11 +33,12 @@ __device__ __forceinline__ void stage1(float (&row)[32], float (&f1)[32], const 
 // stage 2: z2 = acc + b2 -> m = silu(z2), f2; attention gate; row = m * att.  Returns att.
 template <bool KEEP>
 __device__ __forceinline__ float stage2(float (&row)[32], float (&m)[32], float (&f2)[32], const float *vec) {
+  vec = opq(vec);
   float dot = 0.f;
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) {
-    const float4 b = lds4(vec + vB2 * 32 + 4 * k4);
-    const float4 w = lds4(vec + vWA * 32 + 4 * k4);
+    const float4 b = lds4c(vec + vB2 * 32 + 4 * k4);
+    const float4 w = lds4c(vec + vWA * 32 + 4 * k4);
     const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -57,11 +59,12 @@ __device__ __forceinline__ float stage2(float (&row)[32], float (&m)[32], float 
 // stage 3: zc = acc + bc1 -> u = <wc2, silu(zc)>, th = tanh(u); fc = silu'(zc)
 template <bool KEEP>
 __device__ __forceinline__ float stage3(const float (&acc)[32], float (&fc)[32], const float *vec) {
+  vec = opq(vec);
   float u = 0.f;
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) {
-    const float4 b = lds4(vec + vBC1 * 32 + 4 * k4);
-    const float4 w = lds4(vec + vWC2 * 32 + 4 * k4);
+    const float4 b = lds4c(vec + vBC1 * 32 + 4 * k4);
+    const float4 w = lds4c(vec + vWC2 * 32 + 4 * k4);
     const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -76,9 +79,10 @@ __device__ __forceinline__ float stage3(const float (&acc)[32], float (&fc)[32],
 }
 
 __device__ __forceinline__ void add_vec(float (&row)[32], const float *vec32) {
+  vec32 = opq(vec32);
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) {
-    const float4 b = lds4(vec32 + 4 * k4);
+    const float4 b = lds4c(vec32 + 4 * k4);
     row[4 * k4] += b.x; row[4 * k4 + 1] += b.y; row[4 * k4 + 2] += b.z; row[4 * k4 + 3] += b.w;
   }
 }
@@ -95,10 +99,11 @@ __device__ __forceinline__ void embed(float (&h)[32], const float *sEmb, int i, 
 
 // acc = W2 dz1  ->  d(ms) in place:  dm = f2*acc, ds = att(1-att) <wa, dm>, dms = dm*att + m*ds
 __device__ __forceinline__ void tangent_mid(float (&row)[32], const float (&m)[32], const float (&f2)[32], float att, const float *vec) {
+  vec = opq(vec);
   float dsd = 0.f;
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) {
-    const float4 w = lds4(vec + vWA * 32 + 4 * k4);
+    const float4 w = lds4c(vec + vWA * 32 + 4 * k4);
     const float ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -114,10 +119,11 @@ __device__ __forceinline__ void tangent_mid(float (&row)[32], const float (&m)[3
 
 // du = < wc2 * fc, Wc1 dms >
 __device__ __forceinline__ float tangent_du(const float (&acc)[32], const float (&fc)[32], const float *vec) {
+  vec = opq(vec);
   float du = 0.f;
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) {
-    const float4 w = lds4(vec + vWC2 * 32 + 4 * k4);
+    const float4 w = lds4c(vec + vWC2 * 32 + 4 * k4);
     const float ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) du = fmaf(ww[e] * fc[4 * k4 + e], acc[4 * k4 + e], du);
@@ -127,10 +133,11 @@ __device__ __forceinline__ float tangent_du(const float (&acc)[32], const float 
 
 // row = f1 * (row + c1 dr2 + d1 dea)
 __device__ __forceinline__ void tangent_in(float (&row)[32], const float (&f1)[32], const float *vec, float dr2, float dea) {
+  vec = opq(vec);
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) {
-    const float4 c = lds4(vec + vC1 * 32 + 4 * k4);
-    const float4 d = lds4(vec + vD1 * 32 + 4 * k4);
+    const float4 c = lds4c(vec + vC1 * 32 + 4 * k4);
+    const float4 d = lds4c(vec + vD1 * 32 + 4 * k4);
     const float cc[4] = {c.x, c.y, c.z, c.w}, dd[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -142,10 +149,11 @@ __device__ __forceinline__ void tangent_in(float (&row)[32], const float (&f1)[3
 
 // z1 (without the geometric terms) of a layer-0 edge from the class tables:  P0_i + Q0_j
 __device__ __forceinline__ void z1_layer0(float (&row)[32], const float *sCls, float f0i, float f1i, float f0j, float f1j) {
+  sCls = opq(sCls);
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) {
-    const float4 a0 = lds4(sCls + 4 * k4), a1 = lds4(sCls + 32 + 4 * k4), ab = lds4(sCls + 64 + 4 * k4);
-    const float4 b0 = lds4(sCls + 96 + 4 * k4), b1 = lds4(sCls + 128 + 4 * k4), bb = lds4(sCls + 160 + 4 * k4);
+    const float4 a0 = lds4c(sCls + 4 * k4), a1 = lds4c(sCls + 32 + 4 * k4), ab = lds4c(sCls + 64 + 4 * k4);
+    const float4 b0 = lds4c(sCls + 96 + 4 * k4), b1 = lds4c(sCls + 128 + 4 * k4), bb = lds4c(sCls + 160 + 4 * k4);
     row[4 * k4 + 0] = fmaf(f0i, a0.x, fmaf(f1i, a1.x, ab.x)) + fmaf(f0j, b0.x, fmaf(f1j, b1.x, bb.x));
     row[4 * k4 + 1] = fmaf(f0i, a0.y, fmaf(f1i, a1.y, ab.y)) + fmaf(f0j, b0.y, fmaf(f1j, b1.y, bb.y));
     row[4 * k4 + 2] = fmaf(f0i, a0.z, fmaf(f1i, a1.z, ab.z)) + fmaf(f0j, b0.z, fmaf(f1j, b1.z, bb.z));

@@ -102,11 +102,12 @@ __device__ __forceinline__ float dot32r(const float (&a)[32], const float (&b)[3
   }
   return (s0 + s1) + (s2 + s3);
 }
-__device__ __forceinline__ float dot32s(const float (&a)[32], const float *svec) {  // svec in shared memory, 16-byte aligned
+__device__ __forceinline__ float dot32s(const float (&a)[32], const float *svec) {  // svec: constant table in shared memory
+  svec = opq(svec);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) {
-    const float4 q = lds4(svec + 4 * k4);
+    const float4 q = lds4c(svec + 4 * k4);
     s0 = fmaf(a[4 * k4], q.x, s0); s1 = fmaf(a[4 * k4 + 1], q.y, s1);
     s2 = fmaf(a[4 * k4 + 2], q.z, s2); s3 = fmaf(a[4 * k4 + 3], q.w, s3);
   }
@@ -115,11 +116,12 @@ __device__ __forceinline__ float dot32s(const float (&a)[32], const float *svec)
 
 // stage 3 variant: returns tanh(u) and leaves  rowc = wc2 * silu'(zc)  in acc (the operand of the Wc1^T product)
 __device__ __forceinline__ float stage3_v(float (&acc)[32], const float *vec) {
+  vec = opq(vec);
   float u = 0.f;
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) {
-    const float4 b = lds4(vec + vBC1 * 32 + 4 * k4);
-    const float4 w = lds4(vec + vWC2 * 32 + 4 * k4);
+    const float4 b = lds4c(vec + vBC1 * 32 + 4 * k4);
+    const float4 w = lds4c(vec + vWC2 * 32 + 4 * k4);
     const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {

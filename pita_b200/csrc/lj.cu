@@ -239,16 +239,26 @@ lj_pairs_kernel(const float *__restrict__ x, int64_t B, float inv_T, float energ
 
     const f2 eps2 = pk2(kBgflowEps, kBgflowEps);
     f2 e6 = pk2(0.f, 0.f), en3 = pk2(0.f, 0.f);
+    // The streamed pair of step s+1 is loaded BEFORE the reaction stores of step s in program order: loads cannot be moved above
+    // stores that may alias them, so without this every step drains its dependent FMA -> RCP -> FMA chains before the next one's
+    // operands even leave shared memory (r1d ncu: stall_wait 1.7 per issue, FMA pipe 62 %).
+    auto load_pair = [&](int t0, f2 &px, f2 &py, f2 &pz) {
+      const int t1 = t0 + 1;
+      int b0 = g * S + t0; b0 -= (b0 >= NA) ? NA : 0;
+      int b1 = g * S + (t1 <= T ? t1 : t0); b1 -= (b1 >= NA) ? NA : 0;
+      // scalar loads straight into the halves of the packed operands (a vector load would need re-packing moves)
+      px = pk2(lds1(cfg + 3 * b0 + 0), lds1(cfg + 3 * b1 + 0));
+      py = pk2(lds1(cfg + 3 * b0 + 1), lds1(cfg + 3 * b1 + 1));
+      pz = pk2(lds1(cfg + 3 * b0 + 2), lds1(cfg + 3 * b1 + 2));
+    };
+    f2 nbx, nby, nbz;
+    load_pair(1, nbx, nby, nbz);
 #pragma unroll
     for (int t0 = 1; t0 <= T; t0 += 2) {
       const int t1 = t0 + 1;
       const bool has1 = t1 <= T;
-      int b0 = g * S + t0; b0 -= (b0 >= NA) ? NA : 0;
-      int b1 = g * S + (has1 ? t1 : t0); b1 -= (b1 >= NA) ? NA : 0;
-      // scalar loads straight into the halves of the packed operands (a vector load would need re-packing moves)
-      const f2 bx = pk2(lds1(cfg + 3 * b0 + 0), lds1(cfg + 3 * b1 + 0));
-      const f2 by = pk2(lds1(cfg + 3 * b0 + 1), lds1(cfg + 3 * b1 + 1));
-      const f2 bz = pk2(lds1(cfg + 3 * b0 + 2), lds1(cfg + 3 * b1 + 2));
+      const f2 bx = nbx, by = nby, bz = nbz;
+      if (t0 + 2 <= T) load_pair(t0 + 2, nbx, nby, nbz);
       f2 rx = pk2(0.f, 0.f), ry = pk2(0.f, 0.f), rz = pk2(0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < S; ++r) {
@@ -422,6 +432,13 @@ extern "C" int pita_lj_energy_force(const float *x, int64_t B, int n, float temp
       return launch_lj_pairs<13, 1, 4, 3>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
     case 55:
       if (ordered) return launch_lj<55, 8>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+      {  // PITA_LJ_CFG selects alternative mappings of the paired kernel (A/B measurements, profiles/r2j_*)
+        static const int cfg = [] { const char *e = getenv("PITA_LJ_CFG"); return e ? atoi(e) : 0; }();
+        if (cfg == 1) return launch_lj_pairs<55, 11, 1, 3>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+        if (cfg == 2) return launch_lj_pairs<55, 11, 1, 4>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+        if (cfg == 3) return launch_lj_pairs<55, 11, 1, 2>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+        if (cfg == 4) return launch_lj_pairs<55, 5, 2, 1>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+      }
       return launch_lj_pairs<55, 5, 1, 2>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
     default:
       set_error("lj: n_particles=%d unsupported (reference raises NotImplementedError for n not in {13,55}, "

@@ -1,8 +1,10 @@
 """`EnergyNet` with the reference's interface (models/components/energy_net.py).
 
 One CUDA kernel (`pita_egnn_energy`) yields E_theta, grad_x E_theta and dE_theta/dh from a primal forward
-plus a hand-derived reverse pass; nothing here uses autograd.  `pin=True` mixes in the Lennard-Jones
-target exactly as the reference does (:41-48), using the fused LJ energy+force kernel for its gradient."""
+plus a hand-derived reverse pass; nothing here uses autograd.  `pin=True` mixes in the target energy exactly as
+the reference does (:41-48).  NB the reference's target returns `logprobs.detach()` (lennardjones_energy.py:227), so
+the pinned energy's x-gradient carries NO target force — only the (1 - (1-t)^3) share of grad E_theta; pinned to the
+reference by tests/golden/fk_n13_pin.npz."""
 from __future__ import annotations
 
 from typing import Optional
@@ -37,12 +39,10 @@ class EnergyNet(nn.Module):
         de_dt = dh * dh_dt if dh_dt is not None else dh
         if pin:
             assert t is not None and energy_function is not None
-            logp, force = energy_function(xt, return_force=True)
-            u0 = torch.clamp(-logp, max=1e3, min=-1e3)
-            inside = ((-logp) < 1e3) & ((-logp) > -1e3)
+            u0 = torch.clamp(-energy_function(xt), max=1e3, min=-1e3)  # detached in the reference: no d/dx through the target
             w = (1 - t) ** 3
             de_dt = -3 * (1 - t) ** 2 * u0 + 3 * (1 - t) ** 2 * e + (1 - w) * de_dt
-            g = w[:, None] * (-force) * inside[:, None] + (1 - w)[:, None] * g
+            g = (1 - w)[:, None] * g
             e = w * u0 + (1 - w) * e
         return e, g, de_dt
 
