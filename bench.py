@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the annealed Feynman-Kac sampling step (BASELINE.json metric: particle-steps/s).
 
-  python bench.py [--gpus N --steps K --warmup W] [--workload lj55|lj13] [--particles P] [--scaling weak|strong]
+  python bench.py [--gpus N --steps K --warmup W] [--workload lj55|lj13|aldp22] [--particles P] [--scaling weak|strong]
                   [--total-particles T] [--impl ours|reference] [--materialised-noise]
 
 One "step" = one full debiased FK step over all particles through the integrator's public step
@@ -38,7 +38,13 @@ WORKLOADS = {
     "lj13": dict(n=13, particles=1 << 20, chunk=512, sigma_min=0.05, label="LJ-13 annealed FK sampling, 1M particles/GPU (BASELINE configs[1])"),
     # BASELINE.json configs[2]: LJ-55, 256k-4M particles sharded across 1/2/4/8 B200
     "lj55": dict(n=55, particles=1 << 18, chunk=512, sigma_min=0.05, label="LJ-55 annealed FK sampling, 256k particles/GPU (BASELINE configs[2])"),
+    # SURVEY §8 row a8': the alanine-dipeptide denoiser (EGNN_dynamics_AD2_cat, 22 atoms, hidden 64, 5 layers) in the same loop;
+    # the molecular target energy (OpenMM) is out of scope and is not on the pin_energy=False path
+    "aldp22": dict(n=22, particles=1 << 14, chunk=512, sigma_min=0.05, hidden=64, layers=5,
+                   label="ALDP-22 annealed FK sampling (EGNN_dynamics_AD2_cat 64x5), 16k particles/GPU"),
 }
+CPU_SAMPLE = {13: (512, 64), 22: (96, 24), 55: (16, 8)}            # (particles per step, inference chunk) of the host legs
+GPU_ORACLE_SAMPLE = {13: (4096, 512), 22: (512, 64), 55: (64, 16)}  # same for the eager-torch-on-GPU leg
 GAMMA = 4.0 / 3.0  # beta_lower / beta for the 4.0 -> 3.0 rung of the temperature ladder (lj13.yaml:44-50)
 BETA = 0.75
 T_STEP = 0.5       # SDE time of the first timed step (the grid then advances by dt = 1/1000 per step)
@@ -49,6 +55,16 @@ def egnn_macs_forward(n, H=32, L=3):
     """MAC per sample of the reference's dense EGNN forward."""
     E = n * (n - 1)
     return L * (E * ((2 * H + 2) * H + H * H + H + H * H + H) + n * (2 * H * H + H * H))
+
+
+def make_denoiser(wl):
+    if wl["n"] == 22:
+        from pita_b200.egnn_dynamics_ad2_cat import EGNN_dynamics_AD2_cat
+        return EGNN_dynamics_AD2_cat(n_particles=22, n_dimensions=3, hidden_nf=64, n_layers=5, act_fn=torch.nn.SiLU(), recurrent=True,
+                                     attention=True, tanh=True, agg="sum", condition_beta=True)
+    from pita_b200.egnn_temp_conditioned import EGNN_dynamics
+    return EGNN_dynamics(n_particles=wl["n"], n_dimension=3, hidden_nf=32, n_layers=3, act_fn=torch.nn.SiLU(), recurrent=True,
+                         tanh=True, attention=True, condition_time=True, condition_temperature=True, agg="sum")
 
 
 def executed_tensor_macs(n):
@@ -93,15 +109,12 @@ class ClockSampler:
 
 def build_problem(wl, device, seed=12345):
     """Random-init nets with the reference constructors' init (seed 12345, lj13.yaml:11), prior start."""
-    from pita_b200.egnn_temp_conditioned import EGNN_dynamics
     from pita_b200.energy_net import EnergyNet
     from pita_b200.noise_schedules import ElucidatingNoiseSchedule
     from pita_b200.score_net import ScoreNet
     from pita_b200.sdes import VEReverseSDE
     torch.manual_seed(seed)
-    mk = lambda: EGNN_dynamics(n_particles=wl["n"], n_dimension=3, hidden_nf=32, n_layers=3, act_fn=torch.nn.SiLU(),  # noqa: E731
-                               recurrent=True, tanh=True, attention=True, condition_time=True, condition_temperature=True, agg="sum")
-    net_s = mk()
+    net_s = make_denoiser(wl)
     import copy
     net_e = copy.deepcopy(net_s)  # energytemp_module.py:99
     sched = ElucidatingNoiseSchedule(wl["sigma_min"], 80.0, 7.0)
@@ -118,32 +131,32 @@ def oracle_step_seconds(wl, n_particles, steps, threads, device="cpu", chunk=Non
     torch.set_num_threads(threads)
     n = wl["n"]
     chunk = chunk or n_particles
-    with torch.device(device):
-        sd = {k: v.to(device) for k, v in O.random_egnn_state(seed=12345, dtype=torch.float32).items()}
-        sched = O.EDMSchedule(wl["sigma_min"])
-        gen = torch.Generator(device="cpu").manual_seed(0)
-        scale = float((sched.h(torch.tensor(T_STEP, device="cpu")) / GAMMA) ** 0.5)
-        with torch.device("cpu"):
-            x = O.mean_free_prior(n_particles, n, scale, gen=gen)
-        x = x.to(device)
-        g = float(sched.g(torch.tensor(T_STEP, device="cpu")))
-        times = []
-        for _ in range(steps):
-            if device != "cpu":
-                torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            dx, da = [], []
+    state = (O.random_egnn_state(5, 64, seed=12345, dtype=torch.float32, in_nf=23) if n == 22
+             else O.random_egnn_state(seed=12345, dtype=torch.float32))
+    sd = {k: v.to(device) for k, v in state.items()}
+    sched = O.EDMSchedule(wl["sigma_min"])
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    scale = float((sched.h(torch.tensor(T_STEP)) / GAMMA) ** 0.5)
+    x = O.mean_free_prior(n_particles, n, scale, gen=gen).to(device)
+    g = float(sched.g(torch.tensor(T_STEP)))
+    times = []
+    for _ in range(steps):
+        if device != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dx, da = [], []
+        with torch.device(device):  # the oracle creates its per-chunk constants on the default device
             for lo in range(0, n_particles, chunk):  # the reference's inference_batch_size loop (sde_integration.py:312-343)
                 d = O.fk_drift(sd, sd, sched, O.ConstGamma(GAMMA), T_STEP, x[lo:lo + chunk], BETA, n)
                 dx.append(d.drift_x)
                 da.append(d.drift_a)
             drift_x, drift_a = torch.cat(dx), torch.cat(da)
             xn = x + drift_x * 1e-3 + g * torch.randn_like(x) * np.sqrt(1e-3)
-            ids = O.systematic_resample((drift_a * 1e-3).cpu(), 0.5)
-            x = O.centre(xn[torch.from_numpy(ids).to(device)], n).detach()
-            if device != "cpu":
-                torch.cuda.synchronize()
-            times.append(time.perf_counter() - t0)
+        ids = O.systematic_resample((drift_a * 1e-3).cpu(), 0.5)
+        x = O.centre(xn[torch.from_numpy(ids).to(device)], n).detach()
+        if device != "cpu":
+            torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
     return times
 
 
@@ -154,8 +167,8 @@ def run_reference(args, wl):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = args.cpu_particles or (512 if wl["n"] == 13 else 16)
-    chunk = 64 if wl["n"] == 13 else 8  # larger LJ-55 chunks exhaust host memory; chunks run back to back
+    sample, chunk = CPU_SAMPLE[wl["n"]]  # larger LJ-55 chunks exhaust host memory; chunks run back to back
+    sample = args.cpu_particles or sample
     ts = oracle_step_seconds(wl, sample, args.warmup + args.steps, threads, chunk=chunk)[args.warmup:]
     total = sum(ts)
     val = sample * len(ts) / total
@@ -260,7 +273,12 @@ def main():
                                   lightning_module=None, resampling_interval=1, num_negative_time_steps=0, post_mcmc_steps=0,
                                   batch_size=wl["chunk"], fused_noise=fused, collect_logweights=False)
     gam = ConstantAnnealingFactorSchedule(GAMMA)
-    tgt = LennardJonesEnergy(dimensionality=D, n_particles=n)
+    if n in (13, 55):
+        tgt = LennardJonesEnergy(dimensionality=D, n_particles=n)
+    else:  # the molecular target (OpenMM) is out of scope; the pin_energy=False path reads only its shape
+        import types
+        tgt = types.SimpleNamespace(n_particles=n, n_spatial_dim=3, is_molecule=True)
+    Hn, Ln = wl.get("hidden", 32), wl.get("layers", 3)
     scale = float((sched.h(torch.tensor(T_STEP, dtype=torch.float64)) / GAMMA) ** 0.5)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = ops.remove_mean(torch.randn(Nl, D, device=dev, generator=gen) * scale, n)
@@ -310,7 +328,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     k_ms = timed(lambda: sde.score_net.score_and_divergence(ht, x, BETA), 3 if n == 13 else 2, flush)
     en_ms = timed(lambda: sde.energy_net._terms(ht, x, BETA, True, True), 2, flush)
-    alg_flops = (3 * n + 1) * 2.0 * egnn_macs_forward(n) * Nl  # (3n+1) forward-equivalents per particle
+    alg_flops = (3 * n + 1) * 2.0 * egnn_macs_forward(n, Hn, Ln) * Nl  # (3n+1) forward-equivalents per particle
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -337,6 +355,12 @@ def main():
                         "every product (ncu: issue-slot and tensor-pipe utilisation), not by the tensor pipe"
                         % (alg_flops / (2.0 * executed_tensor_macs(n) * Nl))}
 
+    if n == 22:
+        roofline.update({"kernel": "score + exact divergence: ad2_score_div_kernel (fp32 FFMA on the CUDA cores)", "executed_tflops": None,
+                         "note": "achieved = SURVEY 8d algorithmic FLOPs ((3n+1) dense EGNN forwards per particle) / time, against the "
+                                 "tensor peak this GEMM-shaped work should reach; this round the 64x5 network runs as fp32 FFMA matvecs "
+                                 "(one CTA per particle, structured tangents: layer 0 touches only the edges of the perturbed atom)"})
+
     # ---- HBM-bound kernels of the step at this N (algorithmic bytes of SURVEY §8d / achieved GB/s / fraction of the measured peak)
     gu, sc_ = torch.randn_like(x), torch.randn_like(x)
     dv, dh, en = (torch.randn(Nl, device=dev) for _ in range(3))
@@ -359,12 +383,14 @@ def main():
 
     # ---- second half of BASELINE.json's metric: the Lennard-Jones energy+force kernel as a fraction of the FP32 FMA peak
     #      (31 FLOP per unordered pair + 15 per atom), timed alone on this rank's particles, L2 flushed
-    lj_ms = timed(lambda: ops.lj_energy_force(x, n), 5, flush)
     fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
-    lj_tf = (31 * n * (n - 1) // 2 + 15 * n) * Nl / (lj_ms * 1e-3) / 1e12
-    lj_kernel = {"kernel": "lj_pairs_kernel", "configs_per_s": Nl / (lj_ms * 1e-3), "ms": lj_ms, "alg_tflops": lj_tf,
-                 "fp32_peak_tflops": fp32_peak, "fp32_peak_source": "derived: 148 SMs x 128 lanes x 2 FLOP x sm_max_mhz (not in MEASURED_PEAKS.json)",
-                 "frac_fp32_peak": lj_tf / fp32_peak, "alg_gbs": (8 * D + 4) * Nl / (lj_ms * 1e-3) / 1e9}
+    lj_kernel = None
+    if n in (13, 55):
+        lj_ms = timed(lambda: ops.lj_energy_force(x, n), 5, flush)
+        lj_tf = (31 * n * (n - 1) // 2 + 15 * n) * Nl / (lj_ms * 1e-3) / 1e12
+        lj_kernel = {"kernel": "lj_pairs_kernel", "configs_per_s": Nl / (lj_ms * 1e-3), "ms": lj_ms, "alg_tflops": lj_tf,
+                     "fp32_peak_tflops": fp32_peak, "fp32_peak_source": "derived: 148 SMs x 128 lanes x 2 FLOP x sm_max_mhz (not in MEASURED_PEAKS.json)",
+                     "frac_fp32_peak": lj_tf / fp32_peak, "alg_gbs": (8 * D + 4) * Nl / (lj_ms * 1e-3) / 1e9}
 
     # ---- exchange step alone (N > 1): all-gather of a + global softmax/scan/search + peer gather + barriers + all-reduce
     exchange_ms = None
@@ -407,24 +433,20 @@ def main():
     e2e_val = N * KE * S_E2E / (float(e2e_ms.item()) * 1e-3)
     # our kernels per step: energy, phase A x batches, phase B x batches, finalize x batches, sde_fk_step, fk_quantile, resampling
     # (softmax partials / finalize / clip, scan tile sums / offsets / bins, search, change count, gather) = 9
-    from pita_b200 import _native as Nn
-    per = Nn.load().pita_egnn_score_div_workspace_bytes(n, 3) // max(1, 148 * (2 * (128 // n)))
     batches = -(-Nl // (148 * 2 * (128 // n)))
-    launches_per_step = 1 + 3 * batches + 2 + 9
-    del per
+    launches_per_step = (1 + 1 + 2 + 9) if n == 22 else (1 + 3 * batches + 2 + 9)
 
     cpu_baseline = gpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample = args.cpu_particles or (512 if n == 13 else 16)
-        chunk = 64 if n == 13 else 8
+        sample, chunk = CPU_SAMPLE[n]
+        sample = args.cpu_particles or sample
         ts = oracle_step_seconds(wl, sample, 2, threads, chunk=chunk)[1:]
         cpu_baseline = {"value": sample * len(ts) / sum(ts), "unit": "particle-steps/s", "cores": threads, "kind": "port",
                         "sample": "%d particles x %d step (after 1 warm-up) in chunks of %d, torch CPU oracle of the reference path" % (sample, len(ts), chunk)}
     if rank == 0 and not args.no_gpu_baseline:
         try:
-            sample = 4096 if n == 13 else 64
-            chunk = 512 if n == 13 else 16
+            sample, chunk = GPU_ORACLE_SAMPLE[n]
             ts = oracle_step_seconds(wl, sample, 3, os.cpu_count() or 1, device=str(dev), chunk=chunk)[1:]
             gpu_baseline = {"value": sample * len(ts) / sum(ts), "unit": "particle-steps/s", "kind": "oracle port of the reference path, "
                             "plain torch eager on this B200 (vmap(jacrev) divergence, dense [B,n,n] pair tensors)",
@@ -437,8 +459,8 @@ def main():
                 "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["label"], "particles_per_gpu": Nl, "n_atoms": n, "debias_inference": True,
-                           "resampling_interval": 1, "chunk": wl["chunk"], "egnn": "hidden 32, 3 layers, random init seed 12345",
-                           "divergence": ops.default_div_mode(),
+                           "resampling_interval": 1, "chunk": wl["chunk"], "egnn": "hidden %d, %d layers, random init seed 12345" % (Hn, Ln),
+                           "divergence": "fp32" if n == 22 else ops.default_div_mode(),
                            "noise": "in-kernel philox" if fused else "materialised torch.randn",
                            "l2": "inputs (%.0f MB/step working set) larger than L2" % (Nl * D * 4 * 4 / 1e6),
                            "exchange": integ._resampler.exchange},

@@ -329,6 +329,30 @@ def golden_ad2():
         vel = net(t, x, beta)
     out = {"n": n, "x": x.numpy(), "t": t.numpy(), "beta": beta.numpy(), "vel": vel.numpy()}
     out.update({"W." + k: v.detach().float().numpy() for k, v in net.state_dict().items()})
+    # the same network inside the reference's EnergyNet / ScoreNet / VEReverseSDE.f (fp64; energy and score share the weights)
+    torch.set_default_dtype(torch.float64)
+    try:
+        sched = ref.noise.ElucidatingNoiseSchedule(sigma_min=0.05, sigma_max=80, rho=7)
+        en, sn = ref.energy_net.EnergyNet(net), ref.score_net.ScoreNet(net)
+        sde = ref.sdes.VEReverseSDE(sched, energy_net=en, score_net=sn, pin_energy=False, debias_inference=True,
+                                    cdf=lambda h, xx, b_, _f=sn.forward: ref.utils.compute_divergence_exact(_f, h, xx, b_))
+        sde.trainer = FakeTrainer()
+        gs = ref.anneal.ConstantAnnealingFactorSchedule(4.0 / 3.0)
+        t_fk, beta_fk = 0.37, 0.75
+        xs = x * (1.0 + float(sched.h(torch.tensor(t_fk))) ** 0.5 * 0.3)
+        terms = sde.f(torch.tensor(t_fk), xs.clone(), torch.tensor(beta_fk), gs, 1.0, None, resampling_interval=1)
+        ht = sched.h(torch.full((B,), t_fk))
+        xr = xs.clone().requires_grad_(True)
+        out.update({"fk_t": t_fk, "fk_beta": beta_fk, "fk_gamma": 4.0 / 3.0, "fk_x": xs.numpy(), "sigma_min": 0.05,
+                    "drift_X": terms.drift_X.detach().numpy(), "drift_A": terms.drift_A.detach().numpy(),
+                    "div_b": terms.divergence_score.detach().numpy(), "cross": terms.cross_term.detach().numpy(),
+                    "dUt_dt": terms.dUt_dt.detach().numpy(),
+                    "U": en.forward_energy(ht, xr, torch.tensor(beta_fk)).detach().numpy(),
+                    "gradU": en.forward(ht, xr, torch.tensor(beta_fk)).detach().numpy(),
+                    "score": sn.forward(ht, xs, torch.tensor(beta_fk)).detach().numpy(),
+                    "div_score": ref.utils.compute_divergence_exact(sn.forward, ht, xs, torch.tensor(beta_fk)).numpy()})
+    finally:
+        torch.set_default_dtype(torch.float32)
     np.savez_compressed(os.path.join(OUT, "egnn_ad2_n22.npz"), **out)
     print("wrote ad2", float(vel.abs().max()))
 

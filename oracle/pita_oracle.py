@@ -229,13 +229,20 @@ def egnn_velocity_ad2(sd: Dict[str, Tensor], t: Tensor, y: Tensor, beta: Tensor,
     stack as egnn_velocity (recurrent, tanh, attention, agg='sum'; H and L read from the weights: 64 / 5 in
     configs/model/net/egnn_ad2.yaml-style use), but every node carries one_hot(atom type) ++ [t] (++ [beta]) — here the
     time / temperature columns really are per node (:176-186), unlike the interleaving quirk of the LJ network.
-    SURVEY §8 row a8'.  TEST INFRASTRUCTURE: the CUDA path for this network is not built yet."""
+    SURVEY §8 row a8'.  TEST INFRASTRUCTURE (the CUDA path is csrc/egnn_ad2.cu)."""
     B = y.shape[0]
     onehot = torch.nn.functional.one_hot(ad2_atom_types(n)).to(y.dtype)  # [n, 21]
     cols = [onehot[None].expand(B, n, onehot.shape[1]), t[:, None, None].expand(B, n, 1)]
     if condition_beta:
         cols.append(beta[:, None, None].expand(B, n, 1))
     return egnn_velocity(sd, t, y, beta, n, coords_range=coords_range, node_feat=torch.cat(cols, dim=-1))
+
+
+def _velocity(sd, tcond, y, beta, n):
+    """The denoiser the weights belong to: 2 embedding inputs = EGNN_dynamics (LJ), 23 = EGNN_dynamics_AD2_cat."""
+    if sd["egnn.embedding.weight"].shape[1] == 23:
+        return egnn_velocity_ad2(sd, tcond, y, beta, n)
+    return egnn_velocity(sd, tcond, y, beta, n)
 
 
 # --------------------------------------------------------------------------------------
@@ -254,7 +261,7 @@ def model_energy(sd, ht: Tensor, x: Tensor, beta, n: int, precondition_beta=Fals
     beta = beta * torch.ones(x.shape[0], dtype=x.dtype)
     c_s, c_in, c_out, c_noise = _coeffs(ht)
     yy = c_in[:, None] * x
-    u = (egnn_velocity(sd, c_noise, yy, beta, n) * yy).sum(dim=1)
+    u = (_velocity(sd, c_noise, yy, beta, n) * yy).sum(dim=1)
     e = (1 - c_s) / (2 * ht) * torch.linalg.norm(x, dim=-1) ** 2 - c_out / (c_in * ht) * u
     if precondition_beta:
         e = e * beta
@@ -265,7 +272,7 @@ def model_score(sd, ht: Tensor, x: Tensor, beta, n: int, precondition_beta=False
     """ScoreNet.forward (score_net.py:13-43)."""
     beta = beta * torch.ones(x.shape[0], dtype=x.dtype)
     c_s, c_in, c_out, c_noise = _coeffs(ht)
-    den = c_s[:, None] * x + c_out[:, None] * egnn_velocity(sd, c_noise, c_in[:, None] * x, beta, n)
+    den = c_s[:, None] * x + c_out[:, None] * _velocity(sd, c_noise, c_in[:, None] * x, beta, n)
     if precondition_beta:
         den = den * beta[:, None] + (1 - beta[:, None]) * x
     return (den - x) / ht[:, None]
@@ -499,7 +506,7 @@ def md_shaped_coords(num: int, n: int, seed: int, spacing: float = 1.1, jitter: 
 
 
 def random_egnn_state(n_layers: int = 3, hidden: int = 32, seed: int = 12345, dtype=torch.float32,
-                      coord_gain: float = 0.001) -> Dict[str, Tensor]:
+                      coord_gain: float = 0.001, in_nf: int = 2) -> Dict[str, Tensor]:
     """Random-init weights with the reference's parameter names and init distributions
     (nn.Linear default init; xavier_uniform gain 0.001 on the last coord layer,
     egnn_temp_conditioned.py:245-246).  coord_gain can be raised in tests so that the coordinate
@@ -514,7 +521,7 @@ def random_egnn_state(n_layers: int = 3, hidden: int = 32, seed: int = 12345, dt
 
     sd: Dict[str, Tensor] = {}
     H = hidden
-    w, b = lin(H, 2)
+    w, b = lin(H, in_nf)  # 2 = [t, beta] (LJ); 23 = one_hot(atom type) ++ [t, beta] (alanine dipeptide)
     sd["egnn.embedding.weight"], sd["egnn.embedding.bias"] = w, b
     w, b = lin(2, H)
     sd["egnn.embedding_out.weight"], sd["egnn.embedding_out.bias"] = w, b

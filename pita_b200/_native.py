@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpita_b200.so")
-SOURCES = ["capi.cu", "lj.cu", "resample.cu", "sde.cu", "egnn.cu", "egnn_rows.cu", "egnn_tri_a.cu", "egnn_tri_b.cu",
+SOURCES = ["capi.cu", "lj.cu", "resample.cu", "sde.cu", "egnn.cu", "egnn_rows.cu", "egnn_tri_a.cu", "egnn_tri_b.cu", "egnn_ad2.cu",
            "umma_selftest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -659,10 +659,13 @@ static int launch_score(const float *w, const float *ht, const float *x, const f
   return PITA_OK;
 }
 
+static bool is_ad2(int hidden, int layers, int n) { return hidden == 64 && layers == 5 && n == 22; }
+
 static int check_common(const char *what, const float *w, int hidden, int layers, int n, const void *a, const void *b_, const void *c, int64_t B) {
   PITA_REQUIRE(B >= 0, PITA_EINVAL, "%s: negative batch", what);
   PITA_REQUIRE(B == 0 || (w && a && b_ && c), PITA_EINVAL, "%s: null pointer", what);
-  if (hidden != 32 || layers != 3) { set_error("%s: only hidden_nf=32, n_layers=3 (configs/model/net/egnn_temp.yaml) is built; got %d/%d", what, hidden, layers); return PITA_EUNSUP; }
+  if (is_ad2(hidden, layers, n)) return PITA_OK;  // EGNN_dynamics_AD2_cat (csrc/egnn_ad2.cu)
+  if (hidden != 32 || layers != 3) { set_error("%s: only hidden_nf=32, n_layers=3 (egnn_temp.yaml; n = 13 / 55) and hidden_nf=64, n_layers=5, n = 22 (egnn_dynamics_ad2_cat.yaml) are built; got %d/%d", what, hidden, layers); return PITA_EUNSUP; }
   if (n != 13 && n != 55) { set_error("%s: n_particles=%d unsupported (13 or 55)", what, n); return PITA_EUNSUP; }
   return PITA_OK;
 }
@@ -686,11 +689,20 @@ int tri_particles_per_cta_a(int n);
 int64_t workspace_floats_per_particle(int n);
 int64_t workspace_layout(int n, int64_t *out, int max_out);
 }  // namespace tri
+namespace ad2 {
+int64_t pack_floats();
+int launch_forward(const float *w, const float *tc, const float *y, const float *beta, int64_t B, float *vel, cudaStream_t s);
+int launch_energy(const float *w, const float *ht, const float *x, const float *beta, int64_t B, float *e, float *g, float *dh,
+                  cudaStream_t s);
+int launch_score_div(const float *w, const float *ht, const float *x, const float *beta, int64_t B, float *sc, float *dv,
+                     cudaStream_t s);
+}  // namespace ad2
 }  // namespace pita
 
 using namespace pita;
 
 extern "C" int64_t pita_egnn_pack_floats(int hidden, int layers) {
+  if (hidden == 64 && layers == 5) return ad2::pack_floats();
   if (hidden != 32 || layers < 1) return -1;
   return pk::kHeader + (int64_t)layers * pk::kLayer;
 }
@@ -702,6 +714,7 @@ extern "C" int pita_egnn_forward(const float *wpack, int hidden, int layers, int
   if (B == 0) return PITA_OK;
   PITA_REQUIRE(vel, PITA_EINVAL, "egnn_forward: null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (is_ad2(hidden, layers, n)) return ad2::launch_forward(wpack, tcond, y, beta, B, vel, s);
   return launch_forward_rows(n, true, wpack, tcond, y, beta, B, vel, s);
 }
 
@@ -712,6 +725,7 @@ extern "C" int pita_egnn_energy(const float *wpack, int hidden, int layers, int 
   if (B == 0) return PITA_OK;
   PITA_REQUIRE(energy, PITA_EINVAL, "egnn_energy: null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (is_ad2(hidden, layers, n)) return ad2::launch_energy(wpack, ht, x, beta, B, energy, grad_x, dE_dh, s);
   // PITA_ENERGY_ENGINE=simt selects the fp32 CUDA-core kernel (kept for A/B checks); default: tcgen05 row engine, 3xTF32
   static const bool simt = [] { const char *v = getenv("PITA_ENERGY_ENGINE"); return v && strcmp(v, "simt") == 0; }();
   if (simt)
@@ -725,7 +739,7 @@ extern "C" int pita_egnn_energy(const float *wpack, int hidden, int layers, int 
 static int64_t tri_batch(int n) { return (int64_t)kNumSMs * tri::tri_particles_per_cta_a(n); }
 
 extern "C" int64_t pita_egnn_score_div_workspace_bytes(int n, int mode) {
-  if (mode == PITA_DIV_FP32) return 0;
+  if (mode == PITA_DIV_FP32 || n == 22) return 0;  // (the 22-atom network runs on the CUDA cores: no workspace)
   if (n != 13 && n != 55) return -1;
   if (mode == PITA_DIV_BILINEAR) return tri_batch(n) * tri::workspace_floats_per_particle(n) * 4;
   return pita::score_div_rows_workspace_bytes(n);
@@ -745,6 +759,7 @@ extern "C" int pita_egnn_score_div(const float *wpack, int hidden, int layers, i
   PITA_REQUIRE(score, PITA_EINVAL, "egnn_score_div: null output");
   PITA_REQUIRE(mode >= 0 && mode <= 3, PITA_EINVAL, "egnn_score_div: mode must be 0 (fp32), 1 (3xTF32), 2 (TF32) or 3 (bilinear)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (is_ad2(hidden, layers, n)) return ad2::launch_score_div(wpack, ht, x, beta, B, score, div, s);  // fp32 in every mode
   if (mode == PITA_DIV_BILINEAR) {
     if (div == nullptr) return tri::launch_tri_phase_a(n, wpack, ht, x, beta, 0, B, score, nullptr, 0, s);
     const int64_t per = tri::workspace_floats_per_particle(n) * 4;

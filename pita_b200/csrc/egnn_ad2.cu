@@ -1,0 +1,901 @@
+// Alanine-dipeptide EGNN denoiser (BASELINE configs[3]; SURVEY §8 row a8'): EGNN_dynamics_AD2_cat
+// (models/components/egnn_dynamics_ad2_cat.py:158-194) over egnn.EGNN / E_GCL (models/components/egnn.py:108-184) with the
+// configs/model/net/egnn_dynamics_ad2_cat.yaml shape: 22 atoms, hidden 64, 5 layers, SiLU, recurrent, tanh, attention,
+// agg = sum, node features = one_hot(atom type)[21] ++ t ++ beta.
+//
+// Three fp32 CUDA-core kernels, one CTA per particle, warp = receiver node, lane = channel pair (c, c + 32):
+//   forward          vel = EGNN_dynamics_AD2_cat(t, y, beta)
+//   energy           E, grad_x E, dE/dh of EnergyNet (energy_net.py:14-62): primal forward + hand-derived reverse pass
+//   score + div      ScoreNet.forward and tr(d score / dx) (score_net.py:13-43, utils.py:30-51) by forward-mode tangents:
+//                    per tangent node k (three directions) the first layer only touches edges incident to k, the middle
+//                    layers are dense, the last layer only evaluates receiver k (oracle/egnn_analytic.py::trace_dxL_dy)
+// The 64 x 64 weight matrices of a layer do not fit in registers (they do for the 32-wide LJ network, csrc/egnn.cu): they are
+// staged in shared memory per layer and every matvec reads them with conflict-free scalar loads while its input vector(s) are
+// broadcast as float4 — tangent matvecs share one pass over the weights for all three directions.
+// The tcgen05 row engine of the LJ kernels is hard-wired to 32-column TMEM slots; this network runs on the CUDA cores.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace pita {
+namespace ad2 {
+
+constexpr int H = 64;
+constexpr float kCoordsRange = 15.0f;  // EGNN(coords_range=15), egnn.py:120
+constexpr float kNormEps = 1e-8f;      // coord2radial
+
+// ---- packed weight layout (floats).  *_f: [k][c] = W[c][k] (forward product, lane c reads its column coalesced),
+//      *_b: [k][c] = W[k][c] (the transposed product of the reverse pass).
+namespace pk {
+constexpr int kFeat = 23;                 // 21 one-hot atom types, t, beta
+constexpr int kHeader = kFeat * H + H;    // embedding weight [feature][H], bias [H]
+constexpr int M = H * H;
+constexpr int A_f = 0, B_f = M, A_b = 2 * M, B_b = 3 * M, W2_f = 4 * M, W2_b = 5 * M, Wc1_f = 6 * M, Wc1_b = 7 * M,
+              W3h_f = 8 * M, W3h_b = 9 * M, W3a_f = 10 * M, W3a_b = 11 * M, W4_f = 12 * M, W4_b = 13 * M, c1 = 14 * M,
+              d1 = c1 + H, b1 = d1 + H, b2 = b1 + H, wa = b2 + H, ba = wa + H, bc1 = ba + H, wc2 = bc1 + H, b3 = wc2 + H,
+              b4 = b3 + H, kLayer = b4 + H;
+}  // namespace pk
+
+struct V2 {
+  float a, b;  // channels lane and lane + 32
+};
+__device__ __forceinline__ V2 ld2(const float *p, int lane) { return V2{p[lane], p[lane + 32]}; }
+__device__ __forceinline__ void st2(float *p, int lane, V2 v) { p[lane] = v.a; p[lane + 32] = v.b; }
+__device__ __forceinline__ V2 ldg2(const float *__restrict__ p, int lane) { return V2{__ldg(p + lane), __ldg(p + lane + 32)}; }
+__device__ __forceinline__ float wsum2(V2 v) { return warp_sum(v.a + v.b); }
+
+// alanine dipeptide atom typing (egnn_dynamics_ad2_cat.py:67-73): one class per atom except three hydrogen triples
+__device__ __forceinline__ int atom_type22(int i) {
+  if (i == 0 || i == 2 || i == 3) return 2;
+  if (i >= 19) return 20;
+  if (i >= 11 && i <= 13) return 12;
+  return i;
+}
+
+// out[t] = W v_t for NV vectors staged contiguously at vs (each H floats, 16-byte aligned); W: shared memory, layout [k][c]
+template <int NV>
+__device__ __forceinline__ void matvec(const float *W, const float *vs, int lane, V2 (&out)[NV]) {
+#pragma unroll
+  for (int t = 0; t < NV; ++t) out[t] = V2{0.f, 0.f};
+#pragma unroll 4
+  for (int k4 = 0; k4 < H / 4; ++k4) {
+    float4 v[NV];
+#pragma unroll
+    for (int t = 0; t < NV; ++t) v[t] = *reinterpret_cast<const float4 *>(vs + t * H + 4 * k4);
+    const float *w = W + (4 * k4) * H + lane;
+    const float w0a = w[0], w0b = w[32], w1a = w[H], w1b = w[H + 32], w2a = w[2 * H], w2b = w[2 * H + 32], w3a = w[3 * H],
+                w3b = w[3 * H + 32];
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+      out[t].a = fmaf(w0a, v[t].x, fmaf(w1a, v[t].y, fmaf(w2a, v[t].z, fmaf(w3a, v[t].w, out[t].a))));
+      out[t].b = fmaf(w0b, v[t].x, fmaf(w1b, v[t].y, fmaf(w2b, v[t].z, fmaf(w3b, v[t].w, out[t].b))));
+    }
+  }
+}
+
+// cooperative copy of `count` H x H matrices from the packed buffer into shared-memory slots (all threads call)
+struct MatList {
+  const float *p[5];
+  int count;
+};
+__device__ __forceinline__ void load_mats(float *sW, const MatList &ml, int nthreads) {
+  __syncthreads();  // the previous group is no longer read
+  for (int m = 0; m < ml.count; ++m) {
+    const float4 *src = reinterpret_cast<const float4 *>(ml.p[m]);
+    float4 *dst = reinterpret_cast<float4 *>(sW + m * pk::M);
+    for (int q = threadIdx.x; q < pk::M / 4; q += nthreads) dst[q] = __ldg(src + q);
+  }
+  __syncthreads();
+}
+
+struct EdgeScal {
+  V2 c1, d1, b2, wa, bc1, wc2;
+  float ba;
+};
+__device__ __forceinline__ EdgeScal load_edge_scal(const float *__restrict__ Wl, int lane) {
+  EdgeScal s;
+  s.c1 = ldg2(Wl + pk::c1, lane); s.d1 = ldg2(Wl + pk::d1, lane); s.b2 = ldg2(Wl + pk::b2, lane);
+  s.wa = ldg2(Wl + pk::wa, lane); s.bc1 = ldg2(Wl + pk::bc1, lane); s.wc2 = ldg2(Wl + pk::wc2, lane);
+  s.ba = __ldg(Wl + pk::ba);
+  return s;
+}
+
+struct EdgeGeo {
+  float d[3];  // x_i - x_j
+  float r2, nrm, inv, ea;
+};
+__device__ __forceinline__ EdgeGeo edge_geo(const float4 xi, const float4 xj, const float4 x0i, const float4 x0j) {
+  EdgeGeo g;
+  g.d[0] = xi.x - xj.x; g.d[1] = xi.y - xj.y; g.d[2] = xi.z - xj.z;
+  g.r2 = g.d[0] * g.d[0] + g.d[1] * g.d[1] + g.d[2] * g.d[2];
+  g.nrm = sqrtf(g.r2 + kNormEps);
+  g.inv = 1.0f / (g.nrm + 1.0f);
+  const float e0 = x0i.x - x0j.x, e1 = x0i.y - x0j.y, e2 = x0i.z - x0j.z;
+  g.ea = e0 * e0 + e1 * e1 + e2 * e2;
+  return g;
+}
+
+struct EdgeP {
+  V2 f1, f2, fc;  // silu'(z1), silu'(z2), silu'(zc)
+  V2 m, ms;       // m (pre-attention), gated message
+  float s;        // attention gate
+  float th, phi;  // tanh(u), phi = tanh(u) * range
+};
+
+// per-warp staging: primal [2][H] then tangents [2][TTMAX][H]
+template <int TTMAX>
+struct Stage {
+  static constexpr int kFloats = 2 * H + 2 * TTMAX * H;
+  float *pa, *pb, *ta, *tb;
+  __device__ __forceinline__ Stage(float *base) : pa(base), pb(base + H), ta(base + 2 * H), tb(base + 2 * H + TTMAX * H) {}
+};
+
+template <int TT>
+struct EdgeT {
+  V2 dpq[TT > 0 ? TT : 1];
+  float Dd[TT > 0 ? TT : 1][3];
+  float dea[TT > 0 ? TT : 1];
+};
+
+__device__ __forceinline__ V2 silu_both2(V2 z, V2 &der) {
+  V2 v;
+  silu_both(z.a, v.a, der.a);
+  silu_both(z.b, v.b, der.b);
+  return v;
+}
+
+// One edge: primal (edge MLP, attention, coordinate MLP) and TT tangents.  sW2 / sWc1: shared-memory weights ([k][c]).
+template <int TT, int TTMAX>
+__device__ __forceinline__ EdgeP edge_eval(const float *sW2, const float *sWc1, const EdgeScal &sc, float rng, V2 p_plus_q,
+                                           const EdgeGeo &g, const Stage<TTMAX> &st, int lane, const EdgeT<TT> &tin,
+                                           V2 (&dms)[TT > 0 ? TT : 1], float (&dtr)[TT > 0 ? TT : 1][3]) {
+  EdgeP e;
+  const V2 z1 = {p_plus_q.a + sc.c1.a * g.r2 + sc.d1.a * g.ea, p_plus_q.b + sc.c1.b * g.r2 + sc.d1.b * g.ea};
+  const V2 a1 = silu_both2(z1, e.f1);
+  st2(st.pa, lane, a1);
+  float dr2h[TT > 0 ? TT : 1];
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    dr2h[t] = g.d[0] * tin.Dd[t][0] + g.d[1] * tin.Dd[t][1] + g.d[2] * tin.Dd[t][2];
+    const float r2t = 2.0f * dr2h[t];
+    st2(st.ta + t * H, lane, V2{e.f1.a * (tin.dpq[t].a + sc.c1.a * r2t + sc.d1.a * tin.dea[t]),
+                               e.f1.b * (tin.dpq[t].b + sc.c1.b * r2t + sc.d1.b * tin.dea[t])});
+  }
+  __syncwarp();
+  V2 o1[1];
+  matvec<1>(sW2, st.pa, lane, o1);
+  const V2 z2 = {sc.b2.a + o1[0].a, sc.b2.b + o1[0].b};
+  e.m = silu_both2(z2, e.f2);
+  e.s = sigmoidf_fast(wsum2(V2{sc.wa.a * e.m.a, sc.wa.b * e.m.b}) + sc.ba);
+  e.ms = V2{e.m.a * e.s, e.m.b * e.s};
+  st2(st.pb, lane, e.ms);
+  if (TT > 0) {
+    const float s1s = e.s * (1.0f - e.s);
+    V2 ot[TT > 0 ? TT : 1];
+    matvec<(TT > 0 ? TT : 1)>(sW2, st.ta, lane, ot);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      const V2 dm = {e.f2.a * ot[t].a, e.f2.b * ot[t].b};
+      const float ds = s1s * wsum2(V2{sc.wa.a * dm.a, sc.wa.b * dm.b});
+      dms[t] = V2{dm.a * e.s + e.m.a * ds, dm.b * e.s + e.m.b * ds};
+      st2(st.tb + t * H, lane, dms[t]);
+    }
+  }
+  __syncwarp();
+  matvec<1>(sWc1, st.pb, lane, o1);
+  const V2 zc = {sc.bc1.a + o1[0].a, sc.bc1.b + o1[0].b};
+  const V2 ac = silu_both2(zc, e.fc);
+  const float u = wsum2(V2{sc.wc2.a * ac.a, sc.wc2.b * ac.b});
+  e.th = tanhf(u);
+  e.phi = e.th * rng;
+  if (TT > 0) {
+    const float dphi_du = rng * (1.0f - e.th * e.th);
+    const V2 wfc = {sc.wc2.a * e.fc.a, sc.wc2.b * e.fc.b};
+    const float k2 = g.inv * g.inv / g.nrm;
+    V2 ot[TT > 0 ? TT : 1];
+    matvec<(TT > 0 ? TT : 1)>(sWc1, st.tb, lane, ot);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      const float du = wsum2(V2{wfc.a * ot[t].a, wfc.b * ot[t].b});
+      const float dphi = dphi_du * du;
+      const float c = dr2h[t] * k2;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) dtr[t][b] = (tin.Dd[t][b] * g.inv - g.d[b] * c) * e.phi + g.d[b] * g.inv * dphi;
+    }
+  }
+  __syncwarp();
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory plan of the primal state
+// ------------------------------------------------------------------------------------------------
+template <int NP, int NW, int L>
+struct Plan {
+  static constexpr int kThreads = NW * 32;
+  static constexpr int kWMats = 5;                        // weight slots (H x H each)
+  static constexpr int oW = 0;                            // [kWMats][H][H]
+  static constexpr int oX = oW + kWMats * pk::M;          // [L+1][NP][4]
+  static constexpr int oHl = oX + (L + 1) * NP * 4;       // [L][NP][H]   node features entering each layer
+  static constexpr int oZ3 = oHl + L * NP * H;            // [L-1][NP][H] pre-activation of the node MLP
+  static constexpr int oP = oZ3 + (L - 1) * NP * H;       // [NP][H]  A h + b1 of the current layer
+  static constexpr int oQ = oP + NP * H;                  // [NP][H]  B h
+  static constexpr int oAgg = oQ + NP * H;                // [NP][H]
+  static constexpr int oRed = oAgg + NP * H;              // [64]
+  static constexpr int kPrimal = oRed + 64;
+};
+
+template <int NP, int NW>
+__device__ __forceinline__ void node_products(float *sm_P, float *sm_Q, const float *sW_A, const float *sW_B, const float *sHin,
+                                              V2 b1, int lane, int warp) {
+  for (int i = warp; i < NP; i += NW) {
+    V2 o[1];
+    matvec<1>(sW_A, sHin + i * H, lane, o);
+    st2(sm_P + i * H, lane, V2{b1.a + o[0].a, b1.b + o[0].b});
+    matvec<1>(sW_B, sHin + i * H, lane, o);
+    st2(sm_Q + i * H, lane, o[0]);
+  }
+}
+
+// Primal forward of the CTA's particle: sX[0] holds the input coordinates.  On return sX[0..L], sHl[0..L-1], sZ3[0..L-2].
+template <int NP, int NW, int L>
+__device__ void primal_forward(float *sm, const float *__restrict__ wpack, float tcond, float beta, float *stage_base) {
+  using P = Plan<NP, NW, L>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *sW = sm + P::oW;
+  float4 *sX = reinterpret_cast<float4 *>(sm + P::oX);
+  float *sHl = sm + P::oHl, *sZ3 = sm + P::oZ3, *sP = sm + P::oP, *sQ = sm + P::oQ, *sAgg = sm + P::oAgg;
+  Stage<1> st(stage_base + warp * Stage<1>::kFloats);
+  const float rng = kCoordsRange / (float)L;
+  {  // h^0_i = W_emb one_hot(type_i) + t w_t + beta w_beta + b
+    const V2 wt = ldg2(wpack + 21 * H, lane), wb = ldg2(wpack + 22 * H, lane), eb = ldg2(wpack + pk::kFeat * H, lane);
+    for (int i = warp; i < NP; i += NW) {
+      const V2 wc = ldg2(wpack + atom_type22(i) * H, lane);
+      st2(sHl + i * H, lane, V2{wc.a + tcond * wt.a + beta * wb.a + eb.a, wc.b + tcond * wt.b + beta * wb.b + eb.b});
+    }
+  }
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    const float *__restrict__ Wl = wpack + pk::kHeader + l * pk::kLayer;
+    const float *hin = sHl + l * NP * H;
+    MatList g1;
+    g1.p[0] = Wl + pk::A_f; g1.p[1] = Wl + pk::B_f; g1.p[2] = Wl + pk::W2_f; g1.p[3] = Wl + pk::Wc1_f;
+    g1.count = 4;
+    load_mats(sW, g1, P::kThreads);
+    node_products<NP, NW>(sP, sQ, sW, sW + pk::M, hin, ldg2(Wl + pk::b1, lane), lane, warp);
+    __syncthreads();
+    {
+      const EdgeScal sc = load_edge_scal(Wl, lane);
+      EdgeT<0> tin;
+      V2 d0[1];
+      float d1[1][3];
+      for (int i = warp; i < NP; i += NW) {
+        const float4 xi = sX[l * NP + i], x0i = sX[i];
+        const V2 pi = ld2(sP + i * H, lane);
+        V2 agg = {0.f, 0.f};
+        float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < NP; ++j) {
+          if (j == i) continue;
+          const EdgeGeo g = edge_geo(xi, sX[l * NP + j], x0i, sX[j]);
+          const V2 qj = ld2(sQ + j * H, lane);
+          const EdgeP e = edge_eval<0, 1>(sW + 2 * pk::M, sW + 3 * pk::M, sc, rng, V2{pi.a + qj.a, pi.b + qj.b}, g, st, lane, tin, d0, d1);
+          agg.a += e.ms.a; agg.b += e.ms.b;
+          const float f = g.inv * e.phi;
+          dx0 = fmaf(g.d[0], f, dx0); dx1 = fmaf(g.d[1], f, dx1); dx2 = fmaf(g.d[2], f, dx2);
+        }
+        if (lane == 0) sX[(l + 1) * NP + i] = make_float4(xi.x + dx0, xi.y + dx1, xi.z + dx2, 0.f);
+        st2(sAgg + i * H, lane, agg);
+      }
+    }
+    if (l < L - 1) {  // node update (dead code for the output in the last layer)
+      MatList g2;
+      g2.p[0] = Wl + pk::W3h_f; g2.p[1] = Wl + pk::W3a_f; g2.p[2] = Wl + pk::W4_f;
+      g2.count = 3;
+      load_mats(sW, g2, P::kThreads);
+      const V2 b3 = ldg2(Wl + pk::b3, lane), b4 = ldg2(Wl + pk::b4, lane);
+      for (int i = warp; i < NP; i += NW) {
+        V2 o1[1], o2[1];
+        matvec<1>(sW, hin + i * H, lane, o1);
+        matvec<1>(sW + pk::M, sAgg + i * H, lane, o2);
+        const V2 z3 = {b3.a + o1[0].a + o2[0].a, b3.b + o1[0].b + o2[0].b};
+        st2(sZ3 + (l * NP + i) * H, lane, z3);
+        __syncwarp();
+        st2(sAgg + i * H, lane, V2{silu_val(z3.a), silu_val(z3.b)});  // own row: input of the second node linear
+        __syncwarp();
+        matvec<1>(sW + 2 * pk::M, sAgg + i * H, lane, o1);
+        const V2 h0 = ld2(hin + i * H, lane);
+        st2(sHl + ((l + 1) * NP + i) * H, lane, V2{h0.a + b4.a + o1[0].a, h0.b + b4.b + o1[0].b});
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int NP>
+__device__ float4 node_mean(const float4 *x, float *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int i = lane; i < NP; i += 32) { a += x[i].x; b += x[i].y; c += x[i].z; }
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { red[0] = a / NP; red[1] = b / NP; red[2] = c / NP; }
+  }
+  __syncthreads();
+  const float4 m = make_float4(red[0], red[1], red[2], 0.f);
+  __syncthreads();
+  return m;
+}
+
+// ================================================================================================
+// Kernel 1: plain forward
+// ================================================================================================
+template <int NP, int NW, int L>
+__global__ void __launch_bounds__(NW * 32)
+ad2_forward_kernel(const float *__restrict__ wpack, const float *__restrict__ tcond, const float *__restrict__ y,
+                   const float *__restrict__ beta, int64_t B, float *__restrict__ vel) {
+  using P = Plan<NP, NW, L>;
+  extern __shared__ __align__(16) float sm[];
+  float *stage = sm + P::kPrimal;
+  float4 *sX = reinterpret_cast<float4 *>(sm + P::oX);
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int i = threadIdx.x; i < NP; i += P::kThreads)
+      sX[i] = make_float4(y[b * 3 * NP + 3 * i], y[b * 3 * NP + 3 * i + 1], y[b * 3 * NP + 3 * i + 2], 0.f);
+    __syncthreads();
+    primal_forward<NP, NW, L>(sm, wpack, __ldg(tcond + b), __ldg(beta + b), stage);
+    float4 *sV = reinterpret_cast<float4 *>(sm + P::oAgg);
+    for (int i = threadIdx.x; i < NP; i += P::kThreads) {
+      const float4 a = sX[L * NP + i], c = sX[i];
+      sV[i] = make_float4(a.x - c.x, a.y - c.y, a.z - c.z, 0.f);
+    }
+    __syncthreads();
+    const float4 mean = node_mean<NP>(sV, sm + P::oRed);
+    for (int i = threadIdx.x; i < NP; i += P::kThreads) {
+      vel[b * 3 * NP + 3 * i + 0] = sV[i].x - mean.x;
+      vel[b * 3 * NP + 3 * i + 1] = sV[i].y - mean.y;
+      vel[b * 3 * NP + 3 * i + 2] = sV[i].z - mean.z;
+    }
+    __syncthreads();
+  }
+}
+
+// ================================================================================================
+// Kernel 2: energy net — E, grad_x E, dE/dh by a hand-written reverse pass (oracle/egnn_analytic.py::u_theta_backward)
+// ================================================================================================
+template <int NP, int NW, int L>
+struct EPlan {
+  using P = Plan<NP, NW, L>;
+  static constexpr int oGH = P::kPrimal;            // [NP][H]  cotangent of node features
+  static constexpr int oGAgg = oGH + NP * H;        // [NP][H]
+  static constexpr int oGP = oGAgg + NP * H;        // [NP][H]
+  static constexpr int oGQw = oGP + NP * H;         // [NW][NP][H] per-warp private scatter targets (deterministic)
+  static constexpr int oGX = oGQw + NW * NP * H;    // [NP][4]
+  static constexpr int oGXw = oGX + NP * 4;         // [NW][NP][4]
+  static constexpr int oGX0w = oGXw + NW * NP * 4;  // [NW][NP][4]
+  static constexpr int oV = oGX0w + NW * NP * 4;    // [NP][4] velocity before mean removal
+  static constexpr int oStage = oV + NP * 4;
+  static constexpr int kFloats = oStage + NW * Stage<1>::kFloats;
+};
+
+template <int NP, int NW, int L>
+__global__ void __launch_bounds__(NW * 32)
+ad2_energy_kernel(const float *__restrict__ wpack, const float *__restrict__ ht, const float *__restrict__ x,
+                  const float *__restrict__ beta, int64_t B, float *__restrict__ energy, float *__restrict__ grad_x,
+                  float *__restrict__ dE_dh) {
+  using P = Plan<NP, NW, L>;
+  using E = EPlan<NP, NW, L>;
+  extern __shared__ __align__(16) float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *sW = sm + P::oW;
+  float4 *sX = reinterpret_cast<float4 *>(sm + P::oX);
+  float *sHl = sm + P::oHl, *sZ3 = sm + P::oZ3, *sP = sm + P::oP, *sQ = sm + P::oQ, *sRed = sm + P::oRed;
+  float *sGH = sm + E::oGH, *sGAgg = sm + E::oGAgg, *sGP = sm + E::oGP, *sGQw = sm + E::oGQw;
+  float4 *sGX = reinterpret_cast<float4 *>(sm + E::oGX), *sV = reinterpret_cast<float4 *>(sm + E::oV);
+  float *sGXw = sm + E::oGXw, *sGX0w = sm + E::oGX0w;
+  float *stage = sm + E::oStage;
+  Stage<1> st(stage + warp * Stage<1>::kFloats);
+  const float rng = kCoordsRange / (float)L;
+  const bool want_grad = (grad_x != nullptr) || (dE_dh != nullptr);
+
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const float h = __ldg(ht + b);
+    const float c_in = rsqrtf(1.0f + h);
+    const float c_noise = 0.125f * logf(h);
+    for (int i = threadIdx.x; i < NP; i += P::kThreads)
+      sX[i] = make_float4(c_in * x[b * 3 * NP + 3 * i], c_in * x[b * 3 * NP + 3 * i + 1], c_in * x[b * 3 * NP + 3 * i + 2], 0.f);
+    __syncthreads();
+    primal_forward<NP, NW, L>(sm, wpack, c_noise, __ldg(beta + b), stage);
+
+    const float4 ymean = node_mean<NP>(sX, sRed);
+    for (int i = threadIdx.x; i < NP; i += P::kThreads) {
+      const float4 a = sX[L * NP + i], c = sX[i];
+      sV[i] = make_float4(a.x - c.x, a.y - c.y, a.z - c.z, 0.f);
+    }
+    __syncthreads();
+    const float4 vmean = node_mean<NP>(sV, sRed);
+    if (warp == 0) {
+      float u = 0.f, y2 = 0.f;
+      for (int i = lane; i < NP; i += 32) {
+        const float4 yv = sX[i], v = sV[i];
+        u += (v.x - vmean.x) * yv.x + (v.y - vmean.y) * yv.y + (v.z - vmean.z) * yv.z;
+        y2 += yv.x * yv.x + yv.y * yv.y + yv.z * yv.z;
+      }
+      u = warp_sum(u); y2 = warp_sum(y2);
+      if (lane == 0) { sRed[4] = u; sRed[5] = y2; }
+    }
+    __syncthreads();
+    const float U = sRed[4];
+    const float x2 = sRed[5] * (1.0f + h);
+    const float rs_h = rsqrtf(h);
+    if (threadIdx.x == 0) energy[b] = x2 / (2.0f * (1.0f + h)) - rs_h * U;  // energy_net.py:37-39
+    if (!want_grad) { __syncthreads(); continue; }
+
+    // ---- reverse pass.  cotangent on x_L is w_i = y_i - mean(y)
+    for (int i = threadIdx.x; i < NP; i += P::kThreads) {
+      const float4 yv = sX[i];
+      sGX[i] = make_float4(yv.x - ymean.x, yv.y - ymean.y, yv.z - ymean.z, 0.f);
+    }
+    for (int k = threadIdx.x; k < NP * H; k += P::kThreads) { sGH[k] = 0.f; sGAgg[k] = 0.f; }
+    for (int k = threadIdx.x; k < NW * NP * 4; k += P::kThreads) sGX0w[k] = 0.f;
+    __syncthreads();
+
+#pragma unroll 1
+    for (int l = L - 1; l >= 0; --l) {
+      const float *__restrict__ Wl = wpack + pk::kHeader + l * pk::kLayer;
+      const float *hin = sHl + l * NP * H;
+      {  // group 1: node-MLP reverse (W4^T, W3h^T, W3a^T) and this layer's P, Q (A, B)
+        MatList g1;
+        g1.p[0] = Wl + pk::W4_b; g1.p[1] = Wl + pk::W3h_b; g1.p[2] = Wl + pk::W3a_b; g1.p[3] = Wl + pk::A_f; g1.p[4] = Wl + pk::B_f;
+        g1.count = 5;
+        load_mats(sW, g1, P::kThreads);
+      }
+      for (int k = threadIdx.x; k < NW * NP * H; k += P::kThreads) sGQw[k] = 0.f;
+      for (int k = threadIdx.x; k < NW * NP * 4; k += P::kThreads) sGXw[k] = 0.f;
+      if (l < L - 1) {  // gz3 = f3 * (W4^T gh), gh += W3h^T gz3, gagg = W3a^T gz3
+        for (int i = warp; i < NP; i += NW) {
+          V2 o[1], f3;
+          const V2 z3 = ld2(sZ3 + (l * NP + i) * H, lane);
+          silu_both2(z3, f3);
+          matvec<1>(sW, sGH + i * H, lane, o);
+          __syncwarp();
+          st2(sGAgg + i * H, lane, V2{f3.a * o[0].a, f3.b * o[0].b});  // staged in place: only this warp touches row i
+          __syncwarp();
+          V2 o1[1], o2[1];
+          matvec<1>(sW + pk::M, sGAgg + i * H, lane, o1);
+          matvec<1>(sW + 2 * pk::M, sGAgg + i * H, lane, o2);
+          __syncwarp();
+          const V2 gh = ld2(sGH + i * H, lane);
+          st2(sGH + i * H, lane, V2{gh.a + o1[0].a, gh.b + o1[0].b});
+          st2(sGAgg + i * H, lane, o2[0]);
+        }
+      }
+      node_products<NP, NW>(sP, sQ, sW + 3 * pk::M, sW + 4 * pk::M, hin, ldg2(Wl + pk::b1, lane), lane, warp);
+      {  // group 2: edge re-evaluation (W2, Wc1) and cotangents (W2^T, Wc1^T)
+        MatList g2;
+        g2.p[0] = Wl + pk::W2_f; g2.p[1] = Wl + pk::Wc1_f; g2.p[2] = Wl + pk::W2_b; g2.p[3] = Wl + pk::Wc1_b;
+        g2.count = 4;
+        load_mats(sW, g2, P::kThreads);
+      }
+      {
+        const EdgeScal sc = load_edge_scal(Wl, lane);
+        EdgeT<0> tin;
+        V2 d0[1];
+        float d1[1][3];
+        float *gqw = sGQw + warp * NP * H;
+        float *gxw = sGXw + warp * NP * 4;
+        float *gx0w = sGX0w + warp * NP * 4;
+        for (int i = warp; i < NP; i += NW) {
+          const float4 xi = sX[l * NP + i], x0i = sX[i];
+          const V2 pi = ld2(sP + i * H, lane);
+          const float4 gxo = sGX[i];
+          const V2 gagg = ld2(sGAgg + i * H, lane);
+          V2 gp = {0.f, 0.f};
+          float gxi0 = 0.f, gxi1 = 0.f, gxi2 = 0.f, g0i0 = 0.f, g0i1 = 0.f, g0i2 = 0.f;
+#pragma unroll 1
+          for (int j = 0; j < NP; ++j) {
+            if (j == i) continue;
+            const float4 x0j = sX[j];
+            const EdgeGeo g = edge_geo(xi, sX[l * NP + j], x0i, x0j);
+            const V2 qj = ld2(sQ + j * H, lane);
+            const EdgeP e = edge_eval<0, 1>(sW, sW + pk::M, sc, rng, V2{pi.a + qj.a, pi.b + qj.b}, g, st, lane, tin, d0, d1);
+            const float gphi = (gxo.x * g.d[0] + gxo.y * g.d[1] + gxo.z * g.d[2]) * g.inv;
+            const float gu = gphi * rng * (1.0f - e.th * e.th);
+            st2(st.pa, lane, V2{gu * sc.wc2.a * e.fc.a, gu * sc.wc2.b * e.fc.b});
+            __syncwarp();
+            V2 o[1];
+            matvec<1>(sW + 3 * pk::M, st.pa, lane, o);
+            const V2 gms = {gagg.a + o[0].a, gagg.b + o[0].b};
+            const float gs = wsum2(V2{gms.a * e.m.a, gms.b * e.m.b});
+            const float gss = gs * e.s * (1.0f - e.s);
+            const V2 gz2 = {(gms.a * e.s + sc.wa.a * gss) * e.f2.a, (gms.b * e.s + sc.wa.b * gss) * e.f2.b};
+            st2(st.pb, lane, gz2);
+            __syncwarp();
+            matvec<1>(sW + 2 * pk::M, st.pb, lane, o);
+            const V2 gz1 = {o[0].a * e.f1.a, o[0].b * e.f1.b};
+            gp.a += gz1.a; gp.b += gz1.b;
+            gqw[j * H + lane] += gz1.a;
+            gqw[j * H + lane + 32] += gz1.b;
+            const float gr2 = wsum2(V2{sc.c1.a * gz1.a, sc.c1.b * gz1.b});
+            const float gea = wsum2(V2{sc.d1.a * gz1.a, sc.d1.b * gz1.b});
+            const float gd_dot = (gxo.x * g.d[0] + gxo.y * g.d[1] + gxo.z * g.d[2]) * e.phi;
+            const float k2 = gd_dot * g.inv * g.inv / g.nrm;
+            const float a0 = gxo.x * e.phi * g.inv - g.d[0] * k2 + 2.0f * g.d[0] * gr2;
+            const float a1 = gxo.y * e.phi * g.inv - g.d[1] * k2 + 2.0f * g.d[1] * gr2;
+            const float a2 = gxo.z * e.phi * g.inv - g.d[2] * k2 + 2.0f * g.d[2] * gr2;
+            gxi0 += a0; gxi1 += a1; gxi2 += a2;
+            const float e0 = 2.0f * (x0i.x - x0j.x) * gea, e1 = 2.0f * (x0i.y - x0j.y) * gea, e2 = 2.0f * (x0i.z - x0j.z) * gea;
+            g0i0 += e0; g0i1 += e1; g0i2 += e2;
+            if (lane == 0) {
+              gxw[j * 4 + 0] -= a0; gxw[j * 4 + 1] -= a1; gxw[j * 4 + 2] -= a2;
+              gx0w[j * 4 + 0] -= e0; gx0w[j * 4 + 1] -= e1; gx0w[j * 4 + 2] -= e2;
+            }
+            __syncwarp();
+          }
+          st2(sGP + i * H, lane, gp);
+          if (lane == 0) {
+            gxw[i * 4 + 0] += gxi0; gxw[i * 4 + 1] += gxi1; gxw[i * 4 + 2] += gxi2;
+            gx0w[i * 4 + 0] += g0i0; gx0w[i * 4 + 1] += g0i1; gx0w[i * 4 + 2] += g0i2;
+          }
+          __syncwarp();
+        }
+      }
+      {  // group 3: gh_i += A^T gp_i + B^T gq_i ; gx_i += sum_w gxw[w][i]   (fixed order -> deterministic)
+        MatList g3;
+        g3.p[0] = Wl + pk::A_b; g3.p[1] = Wl + pk::B_b;
+        g3.count = 2;
+        load_mats(sW, g3, P::kThreads);
+        for (int i = warp; i < NP; i += NW) {
+          V2 gq = {0.f, 0.f};
+#pragma unroll 1
+          for (int w = 0; w < NW; ++w) { gq.a += sGQw[(w * NP + i) * H + lane]; gq.b += sGQw[(w * NP + i) * H + lane + 32]; }
+          __syncwarp();
+          st2(sGAgg + i * H, lane, gq);  // stage (gagg is dead after the edge pass)
+          __syncwarp();
+          V2 o1[1], o2[1];
+          matvec<1>(sW, sGP + i * H, lane, o1);
+          matvec<1>(sW + pk::M, sGAgg + i * H, lane, o2);
+          const V2 gh = ld2(sGH + i * H, lane);
+          st2(sGH + i * H, lane, V2{gh.a + o1[0].a + o2[0].a, gh.b + o1[0].b + o2[0].b});
+          if (lane < 3) {
+            float acc = 0.f;
+#pragma unroll 1
+            for (int w = 0; w < NW; ++w) acc += sGXw[(w * NP + i) * 4 + lane];
+            reinterpret_cast<float *>(sGX)[i * 4 + lane] += acc;
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- outputs: dU/dy_i = vel_i - w_i + gx_i + gx0_i ;  dU/dtcond = sum_i <gh0_i, w_t>   (every node carries t)
+    float part_dt = 0.f;
+    {
+      const V2 wt = ldg2(wpack + 21 * H, lane);
+      for (int i = warp; i < NP; i += NW) {
+        const V2 gh = ld2(sGH + i * H, lane);
+        part_dt += gh.a * wt.a + gh.b * wt.b;
+      }
+      part_dt = warp_sum(part_dt);
+    }
+    float part_dot = 0.f;
+    for (int i = threadIdx.x; i < NP; i += P::kThreads) {
+      float g0[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int w = 0; w < NW; ++w) {
+        g0[0] += sGX0w[(w * NP + i) * 4 + 0]; g0[1] += sGX0w[(w * NP + i) * 4 + 1]; g0[2] += sGX0w[(w * NP + i) * 4 + 2];
+      }
+      const float4 yv = sX[i], v = sV[i], gx = sGX[i];
+      const float wv[3] = {yv.x - ymean.x, yv.y - ymean.y, yv.z - ymean.z};
+      const float vv[3] = {v.x - vmean.x, v.y - vmean.y, v.z - vmean.z};
+      const float gxx[3] = {gx.x, gx.y, gx.z};
+      const float yy[3] = {yv.x, yv.y, yv.z};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float dUdy = vv[k] - wv[k] + gxx[k] + g0[k];
+        const float xk = yy[k] / c_in;
+        part_dot += dUdy * xk;
+        if (grad_x) grad_x[b * 3 * NP + 3 * i + k] = xk / (1.0f + h) - rs_h * c_in * dUdy;  // energy_net.py:37-39,61
+      }
+    }
+    part_dot = warp_sum(part_dot);
+    __syncthreads();
+    if (lane == 0) { sRed[8 + warp] = part_dt; sRed[8 + NW + warp] = part_dot; }
+    __syncthreads();
+    if (threadIdx.x == 0 && dE_dh) {
+      float dUdc = 0.f, dot = 0.f;
+      for (int w = 0; w < NW; ++w) { dUdc += sRed[8 + w]; dot += sRed[8 + NW + w]; }
+      const float op = 1.0f + h;
+      const float dU_dh = dUdc / (8.0f * h) + dot * (-0.5f) * rsqrtf(op) / op;
+      dE_dh[b] = -x2 / (2.0f * op * op) + 0.5f * rs_h / h * U - rs_h * dU_dh;
+    }
+    __syncthreads();
+  }
+}
+
+// ================================================================================================
+// Kernel 3: score net — score and exact divergence by forward-mode tangents, one tangent node (3 directions) per pass
+// ================================================================================================
+template <int NP, int NW, int L>
+struct DPlan {
+  using P = Plan<NP, NW, L>;
+  static constexpr int T = 3;
+  static constexpr int oDH = P::kPrimal;            // [NP][T][H]  dh entering the current layer
+  static constexpr int oDQ = oDH + NP * T * H;      // [NP][T][H]  B dh (read by every receiver)
+  static constexpr int oDAgg = oDQ + NP * T * H;    // [NP][T][H]  d agg of the current layer (owner rows)
+  static constexpr int oDXa = oDAgg + NP * T * H;   // [NP][T][4]  dx entering the layer
+  static constexpr int oDXb = oDXa + NP * T * 4;    // [NP][T][4]  dx leaving the layer
+  static constexpr int oStage = oDXb + NP * T * 4;
+  static constexpr int kFloats = oStage + NW * Stage<T>::kFloats;
+};
+
+template <int NP, int NW, int L>
+__global__ void __launch_bounds__(NW * 32)
+ad2_score_div_kernel(const float *__restrict__ wpack, const float *__restrict__ ht, const float *__restrict__ x,
+                     const float *__restrict__ beta, int64_t B, float *__restrict__ score, float *__restrict__ divergence) {
+  static_assert(L >= 3, "first / dense / last layer structure");
+  using P = Plan<NP, NW, L>;
+  using Dp = DPlan<NP, NW, L>;
+  constexpr int T = 3;
+  extern __shared__ __align__(16) float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *sW = sm + P::oW;
+  float4 *sX = reinterpret_cast<float4 *>(sm + P::oX);
+  float *sHl = sm + P::oHl, *sZ3 = sm + P::oZ3, *sP = sm + P::oP, *sQ = sm + P::oQ, *sRed = sm + P::oRed;
+  float *sDH = sm + Dp::oDH, *sDQ = sm + Dp::oDQ, *sDAgg = sm + Dp::oDAgg;
+  float4 *sDXa = reinterpret_cast<float4 *>(sm + Dp::oDXa);
+  float4 *sDXb = reinterpret_cast<float4 *>(sm + Dp::oDXb);
+  float *stage = sm + Dp::oStage;
+  Stage<T> st(stage + warp * Stage<T>::kFloats);
+  const float rng = kCoordsRange / (float)L;
+
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const float h = __ldg(ht + b);
+    const float c_in = rsqrtf(1.0f + h), c_s = 1.0f / (1.0f + h), c_out = sqrtf(h) * c_in, c_noise = 0.125f * logf(h);
+    for (int i = threadIdx.x; i < NP; i += P::kThreads)
+      sX[i] = make_float4(c_in * x[b * 3 * NP + 3 * i], c_in * x[b * 3 * NP + 3 * i + 1], c_in * x[b * 3 * NP + 3 * i + 2], 0.f);
+    __syncthreads();
+    primal_forward<NP, NW, L>(sm, wpack, c_noise, __ldg(beta + b), stage);
+    {  // score = ((c_s - 1) x + c_out * vel) / h        (score_net.py:21-43)
+      float4 *sV = reinterpret_cast<float4 *>(sm + P::oAgg);
+      for (int i = threadIdx.x; i < NP; i += P::kThreads) {
+        const float4 a = sX[L * NP + i], c = sX[i];
+        sV[i] = make_float4(a.x - c.x, a.y - c.y, a.z - c.z, 0.f);
+      }
+      __syncthreads();
+      const float4 vmean = node_mean<NP>(sV, sRed);
+      for (int i = threadIdx.x; i < NP; i += P::kThreads) {
+        const float vv[3] = {sV[i].x - vmean.x, sV[i].y - vmean.y, sV[i].z - vmean.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float xv = x[b * 3 * NP + 3 * i + c];
+          score[b * 3 * NP + 3 * i + c] = ((c_s * xv + c_out * vv[c]) - xv) / h;
+        }
+      }
+      __syncthreads();
+    }
+    if (divergence == nullptr) continue;
+
+    float trace = 0.f;  // per-warp partial (uniform across lanes)
+#pragma unroll 1
+    for (int k = 0; k < NP; ++k) {
+      float4 *dxin = sDXa, *dxout = sDXb;
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+        const float *__restrict__ Wl = wpack + pk::kHeader + l * pk::kLayer;
+        const float *hin = sHl + l * NP * H;
+        const bool first = (l == 0), last = (l == L - 1);
+        {
+          MatList g1;
+          g1.p[0] = Wl + pk::A_f; g1.p[1] = Wl + pk::B_f; g1.p[2] = Wl + pk::W2_f; g1.p[3] = Wl + pk::Wc1_f;
+          g1.count = 4;
+          load_mats(sW, g1, P::kThreads);
+        }
+        node_products<NP, NW>(sP, sQ, sW, sW + pk::M, hin, ldg2(Wl + pk::b1, lane), lane, warp);
+        if (!first) {  // dQ_j[a] = B dh_j[a]
+          for (int j = warp; j < NP; j += NW) {
+            V2 o[T];
+            matvec<T>(sW + pk::M, sDH + j * T * H, lane, o);
+#pragma unroll
+            for (int t = 0; t < T; ++t) st2(sDQ + (j * T + t) * H, lane, o[t]);
+          }
+        }
+        __syncthreads();
+        const EdgeScal sc = load_edge_scal(Wl, lane);
+        if (!last) {
+          // ---- every receiver i (owner warp): the edges (i, j) that carry a tangent
+          for (int i = warp; i < NP; i += NW) {
+            V2 dp[T], dagg[T];
+            float dxi[T][3], dxo[T][3];
+            if (first) {
+#pragma unroll
+              for (int t = 0; t < T; ++t) {
+                dp[t] = V2{0.f, 0.f};
+                dxi[t][0] = dxi[t][1] = dxi[t][2] = 0.f;
+                if (i == k) dxi[t][t] = 1.0f;
+              }
+            } else {
+              matvec<T>(sW, sDH + i * T * H, lane, dp);
+#pragma unroll
+              for (int t = 0; t < T; ++t) {
+                const float4 q = dxin[i * T + t];
+                dxi[t][0] = q.x; dxi[t][1] = q.y; dxi[t][2] = q.z;
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              dagg[t] = V2{0.f, 0.f};
+              dxo[t][0] = dxi[t][0]; dxo[t][1] = dxi[t][1]; dxo[t][2] = dxi[t][2];  // identity path x' = x + ...
+            }
+            const float4 xi = sX[l * NP + i], x0i = sX[i];
+            const V2 pi = ld2(sP + i * H, lane);
+#pragma unroll 1
+            for (int j = 0; j < NP; ++j) {
+              if (j == i) continue;
+              if (first && i != k && j != k) continue;  // layer 0: only edges incident to the tangent node
+              const float4 x0j = sX[j];
+              const EdgeGeo g = edge_geo(xi, sX[l * NP + j], x0i, x0j);
+              const V2 qj = ld2(sQ + j * H, lane);
+              EdgeT<T> tin;
+              const float e0[3] = {x0i.x - x0j.x, x0i.y - x0j.y, x0i.z - x0j.z};
+              const float sgn = (i == k) ? 1.0f : ((j == k) ? -1.0f : 0.0f);
+#pragma unroll
+              for (int t = 0; t < T; ++t) {
+                if (first) {
+                  tin.dpq[t] = V2{0.f, 0.f};
+                  tin.Dd[t][0] = t == 0 ? sgn : 0.f; tin.Dd[t][1] = t == 1 ? sgn : 0.f; tin.Dd[t][2] = t == 2 ? sgn : 0.f;
+                } else {
+                  const V2 dq = ld2(sDQ + (j * T + t) * H, lane);
+                  tin.dpq[t] = V2{dp[t].a + dq.a, dp[t].b + dq.b};
+                  const float4 q = dxin[j * T + t];
+                  tin.Dd[t][0] = dxi[t][0] - q.x; tin.Dd[t][1] = dxi[t][1] - q.y; tin.Dd[t][2] = dxi[t][2] - q.z;
+                }
+                tin.dea[t] = 2.0f * sgn * e0[t];  // d edge_attr: only edges incident to the tangent node
+              }
+              V2 dms[T];
+              float dtr[T][3];
+              edge_eval<T, T>(sW + 2 * pk::M, sW + 3 * pk::M, sc, rng, V2{pi.a + qj.a, pi.b + qj.b}, g, st, lane, tin, dms, dtr);
+#pragma unroll
+              for (int t = 0; t < T; ++t) {
+                dagg[t].a += dms[t].a; dagg[t].b += dms[t].b;
+                dxo[t][0] += dtr[t][0]; dxo[t][1] += dtr[t][1]; dxo[t][2] += dtr[t][2];
+              }
+            }
+            if (lane < T) {
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int t = 0; t < T; ++t)
+                if (t == lane) o = make_float4(dxo[t][0], dxo[t][1], dxo[t][2], 0.f);
+              dxout[i * T + lane] = o;
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) st2(sDAgg + (i * T + t) * H, lane, dagg[t]);
+          }
+          // ---- node update on the tangents: dz3 = W3h dh + W3a dagg ; dh' = dh + W4 (f3 * dz3)      (dh = 0 entering layer 0)
+          {
+            MatList g2;
+            g2.p[0] = Wl + pk::W3h_f; g2.p[1] = Wl + pk::W3a_f; g2.p[2] = Wl + pk::W4_f;
+            g2.count = 3;
+            load_mats(sW, g2, P::kThreads);
+          }
+          for (int i = warp; i < NP; i += NW) {
+            V2 f3, dz3[T], o[T];
+            silu_both2(ld2(sZ3 + (l * NP + i) * H, lane), f3);
+            matvec<T>(sW + pk::M, sDAgg + i * T * H, lane, dz3);
+            if (!first) {
+              matvec<T>(sW, sDH + i * T * H, lane, o);
+#pragma unroll
+              for (int t = 0; t < T; ++t) { dz3[t].a += o[t].a; dz3[t].b += o[t].b; }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < T; ++t) st2(sDAgg + (i * T + t) * H, lane, V2{f3.a * dz3[t].a, f3.b * dz3[t].b});  // own rows
+            __syncwarp();
+            matvec<T>(sW + 2 * pk::M, sDAgg + i * T * H, lane, o);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              V2 dh = first ? V2{0.f, 0.f} : ld2(sDH + (i * T + t) * H, lane);
+              st2(sDH + (i * T + t) * H, lane, V2{dh.a + o[t].a, dh.b + o[t].b});
+            }
+          }
+          __syncthreads();
+          float4 *tmp = dxin;
+          dxin = dxout;
+          dxout = tmp;
+        } else {
+          // ---- last layer: receiver k only; its edges (k, j) are spread over the warps by sender
+          V2 dp[T];
+          matvec<T>(sW, sDH + k * T * H, lane, dp);
+          const float4 xk = sX[l * NP + k], x0k = sX[k];
+          const V2 pk_ = ld2(sP + k * H, lane);
+          for (int j = warp; j < NP; j += NW) {
+            if (j == k) {  // identity path x^L_k = x^{L-1}_k + ...
+              trace += dxin[k * T + 0].x + dxin[k * T + 1].y + dxin[k * T + 2].z;
+              continue;
+            }
+            const float4 x0j = sX[j];
+            const EdgeGeo g = edge_geo(xk, sX[l * NP + j], x0k, x0j);
+            const V2 qj = ld2(sQ + j * H, lane);
+            EdgeT<T> tin;
+            const float e0[3] = {x0k.x - x0j.x, x0k.y - x0j.y, x0k.z - x0j.z};
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const V2 dq = ld2(sDQ + (j * T + t) * H, lane);
+              tin.dpq[t] = V2{dp[t].a + dq.a, dp[t].b + dq.b};
+              const float4 qk = dxin[k * T + t], qq = dxin[j * T + t];
+              tin.Dd[t][0] = qk.x - qq.x; tin.Dd[t][1] = qk.y - qq.y; tin.Dd[t][2] = qk.z - qq.z;
+              tin.dea[t] = 2.0f * e0[t];
+            }
+            V2 dms[T];
+            float dtr[T][3];
+            edge_eval<T, T>(sW + 2 * pk::M, sW + 3 * pk::M, sc, rng, V2{pk_.a + qj.a, pk_.b + qj.b}, g, st, lane, tin, dms, dtr);
+            trace += dtr[0][0] + dtr[1][1] + dtr[2][2];
+          }
+          __syncthreads();
+        }
+      }
+    }
+    // ---- reduce the per-warp traces (fixed order):  div = ((c_s-1) D + c_out c_in (tr - D)) / h
+    if (lane == 0) sRed[8 + warp] = trace;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tr = 0.f;
+      for (int w = 0; w < NW; ++w) tr += sRed[8 + w];
+      const float Dn = (float)(3 * NP);
+      divergence[b] = ((c_s - 1.0f) * Dn + c_out * c_in * (tr - Dn)) / h;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+template <typename K>
+static int set_smem(K kernel, size_t bytes, const char *name) {
+  if (bytes > 227 * 1024) { set_error("%s needs %zu bytes of shared memory (> 227 KB)", name, bytes); return PITA_EUNSUP; }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e)); return PITA_ECUDA; }
+  return PITA_OK;
+}
+static inline unsigned grid_for(int64_t B) { return (unsigned)(B < kNumSMs ? B : kNumSMs); }
+
+constexpr int kNP = 22, kNW = 8, kL = 5;
+
+int64_t pack_floats() { return pk::kHeader + (int64_t)kL * pk::kLayer; }
+
+int launch_forward(const float *w, const float *tc, const float *y, const float *beta, int64_t B, float *vel, cudaStream_t s) {
+  using P = Plan<kNP, kNW, kL>;
+  const size_t bytes = (P::kPrimal + kNW * Stage<1>::kFloats) * sizeof(float);
+  auto k = ad2_forward_kernel<kNP, kNW, kL>;
+  int rc = set_smem(k, bytes, "ad2_forward_kernel");
+  if (rc) return rc;
+  k<<<grid_for(B), kNW * 32, bytes, s>>>(w, tc, y, beta, B, vel);
+  PITA_CHECK_LAUNCH("ad2_forward_kernel");
+  return PITA_OK;
+}
+int launch_energy(const float *w, const float *ht, const float *x, const float *beta, int64_t B, float *e, float *g, float *dh,
+                  cudaStream_t s) {
+  using E = EPlan<kNP, kNW, kL>;
+  const size_t bytes = E::kFloats * sizeof(float);
+  auto k = ad2_energy_kernel<kNP, kNW, kL>;
+  int rc = set_smem(k, bytes, "ad2_energy_kernel");
+  if (rc) return rc;
+  k<<<grid_for(B), kNW * 32, bytes, s>>>(w, ht, x, beta, B, e, g, dh);
+  PITA_CHECK_LAUNCH("ad2_energy_kernel");
+  return PITA_OK;
+}
+int launch_score_div(const float *w, const float *ht, const float *x, const float *beta, int64_t B, float *sc, float *dv,
+                     cudaStream_t s) {
+  using Dp = DPlan<kNP, kNW, kL>;
+  const size_t bytes = Dp::kFloats * sizeof(float);
+  auto k = ad2_score_div_kernel<kNP, kNW, kL>;
+  int rc = set_smem(k, bytes, "ad2_score_div_kernel");
+  if (rc) return rc;
+  k<<<grid_for(B), kNW * 32, bytes, s>>>(w, ht, x, beta, B, sc, dv);
+  PITA_CHECK_LAUNCH("ad2_score_div_kernel");
+  return PITA_OK;
+}
+
+}  // namespace ad2
+}  // namespace pita
