@@ -90,6 +90,13 @@ __device__ __forceinline__ void sts4(float *p, float4 v) {
                "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+// 16-byte asynchronous global -> shared copies (LDGSTS): issue, commit as one group, wait for every group of this thread
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ float lds1(const float *p) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))) : "memory");

@@ -246,6 +246,7 @@ __device__ void primal_forward(float *sm, const float *__restrict__ wpack, float
       for (int i = warp; i < NP; i += NW) {
         const float z3 = b3 + dot32(wa_, sH + i * H) + dot32(wb_, sAgg + i * H);
         sZ3[(l * NP + i) * H + lane] = z3;
+        __syncwarp();                       // every lane has read row i of sAgg (racecheck: profiles/r2p_racecheck_*.txt)
         sAgg[i * H + lane] = silu_val(z3);  // reuse as the input of the second node linear
       }
       __syncwarp();

@@ -382,6 +382,280 @@ lj_pairs_kernel(const float *__restrict__ x, int64_t B, float inv_T, float energ
   }
 }
 
+// =============================================================================================================
+// "Blocked" paired kernel (default for LJ-55).  Same arithmetic per unordered pair as lj_pairs_kernel, different work split:
+//   * G = 8 atom groups of S = 7 (55 atoms + one ghost parked at 1e15, whose pair terms flush to exactly 0),
+//     warp = group, lane = configuration: 8 warps per CTA and two CTAs per SM = 16 warps, four on every warp scheduler.
+//     Why: the five-warp CTAs of lj_pairs_kernel<55,5,..> load the four schedulers 3:3:2:2 at best (10/12 = 83 %, the
+//     measured ceiling of the pair chain at 5 x 2 warps, profiles/r2o_ubench_lj_chain.txt) and ptxas emits each pair's
+//     FMA -> MUFU.RCP -> FMUL -> FMA chain back to back, so with 2.5 warps per scheduler the FMA pipe idles 38 % of the
+//     time (profiles/r1d_ncu_lj55.txt).  The same chain at 16 warps per SM reaches 96 % in the micro-benchmark without
+//     any help from the instruction scheduler.
+//   * the unordered pairs are tiled by group: thread g evaluates its own triangle (21 pairs), the three rectangles
+//     (g, g+1), (g, g+2), (g, g+3) in full (49 pairs each) and its share of (g, g+4): groups 0-3 take their seven atoms
+//     against atoms 0-3 of group g+4, groups 4-7 their atoms 4-6 against all seven atoms of group g-4.
+//   * reactions on streamed atoms leave through shared memory, one slot per group offset (1, 2, 3, 4): every slot entry
+//     has one writer and the gather order is fixed -- deterministic, no atomics.  The position rows of a tile double as the
+//     coalescing stage of its force rows.
+//   * NOT persistent: a two-CTA-per-SM persistent variant with cp.async double buffering and two reaction slots measured
+//     8 % slower (profiles/r2s_lj_ab_persistent_variant.txt) -- co-resident persistent CTAs run their barrier / gather / copy-out phases in
+//     lock step, while independently scheduled CTAs drift apart and fill each other's bubbles.
+// =============================================================================================================
+constexpr float kGhost = 1e15f;   // a padding atom this far away contributes exactly 0 to every sum (1/s^2 underflows)
+
+template <int NA>
+struct LJBlockCfg {
+  static constexpr int G = 8, S = 7, NP = G * S;       // padded atom count
+  static_assert(NA == 55, "the blocked kernel is laid out for 55 atoms (56 = 8 x 7 with one ghost)");
+  static constexpr int CPB = 32, kThreads = 32 * G;
+  static constexpr int kPitch = 3 * NA;                // the global layout; odd pitch: lane = configuration is bank-conflict free
+  static constexpr int kPosFloats = CPB * kPitch + 4;  // (+ the three floats a ghost load of the last row touches)
+  static constexpr int kSlots = 4;
+  static constexpr int kReactFloats = kSlots * NP * 3 * CPB;   // [slot][atom][xyz][lane]
+  static constexpr int kSmemBytes = (kPosFloats + kReactFloats) * 4 + G * CPB * 16 + G * CPB * 4;
+};
+
+// One packed step: two streamed atoms (lo / hi halves of bx, by, bz) against the own atoms r in [LO0, HI0] (lo half) and
+// [LO1, HI1] (hi half; HI1 < LO1 = no second atom).  Accumulates the owners' force sums and the pair energies and returns
+// the reactions on the two streamed atoms in (rx, ry, rz).
+template <int S, int LO0, int HI0, int LO1, int HI1, bool FORCE>
+__device__ __forceinline__ void lj_block_step(const float (&ax)[S], const float (&ay)[S], const float (&az)[S], f2 (&fx)[S],
+                                              f2 (&fy)[S], f2 (&fz)[S], f2 bx, f2 by, f2 bz, f2 &e6, f2 &en3, f2 &rx, f2 &ry,
+                                              f2 &rz) {
+  const f2 eps2 = pk2(kBgflowEps, kBgflowEps);
+  rx = pk2(0.f, 0.f); ry = rx; rz = rx;
+#pragma unroll
+  for (int r = 0; r < S; ++r) {
+    const bool v0 = r >= LO0 && r <= HI0, v1 = r >= LO1 && r <= HI1;
+    if (v0 || v1) {
+      const f2 dx = sub2(pk2(ax[r], ax[r]), bx), dy = sub2(pk2(ay[r], ay[r]), by), dz = sub2(pk2(az[r], az[r]), bz);
+      f2 s = fma2(dx, dx, eps2);
+      s = fma2(dy, dy, s);
+      s = fma2(dz, dz, s);
+      if (!v0) s = add2(s, pk2(1e30f, 0.f));
+      if (!v1) s = add2(s, pk2(0.f, 1e30f));
+      float s_lo, s_hi;
+      unpk2(s, s_lo, s_hi);
+      const f2 ninv = pk2(fast_rcp(-s_lo), fast_rcp(-s_hi));   // -1/s
+      const f2 inv2 = mul2(ninv, ninv);                         //  1/s^2
+      const f2 ni3 = mul2(inv2, ninv);                          // -1/s^3
+      e6 = fma2(ni3, ni3, e6);                                  // sum r^-12
+      en3 = add2(en3, ni3);                                     // -sum r^-6
+      if (FORCE) {
+        const f2 w = mul2(inv2, inv2);                          //  1/s^4
+        const f2 nfs = fma2(w, ni3, w);                         // -(s^-6 - s^-3)/s
+        fx[r] = fma2(nfs, dx, fx[r]); fy[r] = fma2(nfs, dy, fy[r]); fz[r] = fma2(nfs, dz, fz[r]);
+        rx = fma2(nfs, dx, rx); ry = fma2(nfs, dy, ry); rz = fma2(nfs, dz, rz);
+      }
+    }
+  }
+}
+
+#pragma nv_diag_suppress 549   // own-atom registers are set and used only by active lanes
+template <int NA, bool FORCE>
+__global__ void __launch_bounds__(LJBlockCfg<NA>::kThreads, 2)
+lj_blocked_kernel(const float *__restrict__ x, int64_t B, float inv_T, float energy_factor, float osc,
+                  float *__restrict__ logp, float *__restrict__ force) {
+  using C = LJBlockCfg<NA>;
+  constexpr int S = C::S, G = C::G, NP = C::NP, D = 3 * NA, P = C::kPitch;
+  constexpr int NV = C::CPB * D / 4, PER = (NV + C::kThreads - 1) / C::kThreads;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *s_pos = reinterpret_cast<float *>(smem_raw);          // [CPB][3*NA], the global layout
+  float *s_react = s_pos + C::kPosFloats;                      // [slot][atom][xyz][lane]
+  float4 *s_part = reinterpret_cast<float4 *>(s_react + C::kReactFloats);   // [G][CPB] centre-of-mass partial sums
+  float *s_en = reinterpret_cast<float *>(s_part + G * C::CPB);               // [G][CPB] energy partial sums
+
+  const int tid = threadIdx.x, c = tid & 31, g = tid >> 5;
+  const int a0 = g * S;
+  {
+    const int tile = blockIdx.x;
+    const int ncfg = (int)min((int64_t)C::CPB, B - (int64_t)tile * C::CPB);
+    const int nflt = ncfg * D;
+    const float *__restrict__ src = x + (int64_t)tile * C::CPB * D;
+    if (ncfg == C::CPB) {   // full tile: every load is issued before the first store (a plain loop waits for each in turn)
+      float4 buf[PER];
+#pragma unroll
+      for (int k = 0; k < PER; ++k)
+        if (tid + k * C::kThreads < NV) buf[k] = __ldg(reinterpret_cast<const float4 *>(src) + tid + k * C::kThreads);
+#pragma unroll
+      for (int k = 0; k < PER; ++k)
+        if (tid + k * C::kThreads < NV) reinterpret_cast<float4 *>(s_pos)[tid + k * C::kThreads] = buf[k];
+    } else {
+      for (int f = tid; f < nflt; f += C::kThreads) s_pos[f] = __ldg(src + f);
+    }
+    __syncthreads();
+
+    const bool active = c < ncfg;
+    const float *__restrict__ cfg = s_pos + c * P;
+    float ax[S], ay[S], az[S];
+    f2 fx[S], fy[S], fz[S];
+    f2 e6 = pk2(0.f, 0.f), en3 = pk2(0.f, 0.f), rx, ry, rz;
+    float xl, xh, yl, yh, zl, zh;
+    f2 bx, by, bz, nx, ny, nz;
+#define PITA_UNPACK_R() do { unpk2(rx, xl, xh); unpk2(ry, yl, yh); unpk2(rz, zl, zh); } while (0)
+    // streamed atom q of the rectangles: group g + 1 + q/7 (mod 8), atom q % 7 of it
+    auto rect_atom = [&](int q) { int gb = g + 1 + q / S; gb -= (gb >= G) ? G : 0; return gb * S + q % S; };
+    auto half_atom = [&](int u) { int gb = g + 4; gb -= (gb >= G) ? G : 0; return gb * S + u; };
+    // atom index NA is the ghost: its coordinates are replaced after the load (warp-uniform select)
+    auto load2 = [&](int b0, int b1, f2 &px, f2 &py, f2 &pz) {
+      float x0 = lds1(cfg + 3 * b0 + 0), y0 = lds1(cfg + 3 * b0 + 1), z0 = lds1(cfg + 3 * b0 + 2);
+      float x1 = lds1(cfg + 3 * b1 + 0), y1 = lds1(cfg + 3 * b1 + 1), z1 = lds1(cfg + 3 * b1 + 2);
+      if (b0 == NA) { x0 = kGhost; y0 = kGhost; z0 = kGhost; }
+      if (b1 == NA) { x1 = kGhost; y1 = kGhost; z1 = kGhost; }
+      px = pk2(x0, x1); py = pk2(y0, y1); pz = pk2(z0, z1);
+    };
+    // Reactions: slot = group offset - 1; every slot entry has exactly one writer.
+    auto put = [&](int slot, int atom, float vx, float vy, float vz) {
+      float *d = s_react + ((slot * NP + atom) * 3) * C::CPB + c;
+      d[0] = vx; d[C::CPB] = vy; d[2 * C::CPB] = vz;
+    };
+    auto own_react = [&](int r, float vx, float vy, float vz) {   // the owner's accumulator carries -P
+      float lo, hi;
+      unpk2(fx[r], lo, hi); fx[r] = pk2(lo - vx, hi);
+      unpk2(fy[r], lo, hi); fy[r] = pk2(lo - vy, hi);
+      unpk2(fz[r], lo, hi); fz[r] = pk2(lo - vz, hi);
+    };
+
+    if (active) {
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        ax[r] = cfg[3 * (a0 + r) + 0]; ay[r] = cfg[3 * (a0 + r) + 1]; az[r] = cfg[3 * (a0 + r) + 2];
+        const bool real = (r < S - 1) || (g < G - 1);
+        if (real) { sx += ax[r]; sy += ay[r]; sz += az[r]; }
+        else { ax[r] = kGhost; ay[r] = kGhost; az[r] = kGhost; }   // (the load read the next row / the pad: any value)
+        fx[r] = pk2(0.f, 0.f); fy[r] = pk2(0.f, 0.f); fz[r] = pk2(0.f, 0.f);
+      }
+      s_part[g * C::CPB + c] = make_float4(sx, sy, sz, 0.f);
+
+      // ---- own triangle: streamed atom u against own atoms r < u, two at a time (operands straight from registers)
+      lj_block_step<S, 0, 0, 0, 1, FORCE>(ax, ay, az, fx, fy, fz, pk2(ax[1], ax[2]), pk2(ay[1], ay[2]), pk2(az[1], az[2]), e6, en3, rx, ry, rz);
+      if (FORCE) { PITA_UNPACK_R(); own_react(1, xl, yl, zl); own_react(2, xh, yh, zh); }
+      lj_block_step<S, 0, 2, 0, 3, FORCE>(ax, ay, az, fx, fy, fz, pk2(ax[3], ax[4]), pk2(ay[3], ay[4]), pk2(az[3], az[4]), e6, en3, rx, ry, rz);
+      if (FORCE) { PITA_UNPACK_R(); own_react(3, xl, yl, zl); own_react(4, xh, yh, zh); }
+      lj_block_step<S, 0, 4, 0, 5, FORCE>(ax, ay, az, fx, fy, fz, pk2(ax[5], ax[6]), pk2(ay[5], ay[6]), pk2(az[5], az[6]), e6, en3, rx, ry, rz);
+      if (FORCE) { PITA_UNPACK_R(); own_react(5, xl, yl, zl); own_react(6, xh, yh, zh); }
+
+      // ---- rectangles (g, g+1..3): streamed atoms 0..19 (atom 20 rides with the half rectangle); the next pair is loaded
+      //      before this pair's reaction stores (loads cannot be hoisted above stores that may alias them)
+      load2(rect_atom(0), rect_atom(1), nx, ny, nz);
+#pragma unroll
+      for (int q = 0; q < 20; q += 2) {
+        bx = nx; by = ny; bz = nz;
+        if (q + 2 < 20) load2(rect_atom(q + 2), rect_atom(q + 3), nx, ny, nz);
+        lj_block_step<S, 0, S - 1, 0, S - 1, FORCE>(ax, ay, az, fx, fy, fz, bx, by, bz, e6, en3, rx, ry, rz);
+        if (FORCE) {
+          PITA_UNPACK_R();
+          put(q / S, rect_atom(q), xl, yl, zl);
+          put((q + 1) / S, rect_atom(q + 1), xh, yh, zh);
+        }
+      }
+      // ---- the last rectangle atom and this thread's share of the (g, g+4) rectangle
+      if (g < G / 2) {   // own atoms 0..6 against atoms 0..3 of group g+4
+        load2(rect_atom(20), half_atom(0), bx, by, bz);
+        load2(half_atom(1), half_atom(2), nx, ny, nz);
+        lj_block_step<S, 0, S - 1, 0, S - 1, FORCE>(ax, ay, az, fx, fy, fz, bx, by, bz, e6, en3, rx, ry, rz);
+        load2(half_atom(3), half_atom(3), bx, by, bz);
+        if (FORCE) { PITA_UNPACK_R(); put(2, rect_atom(20), xl, yl, zl); put(3, half_atom(0), xh, yh, zh); }
+        lj_block_step<S, 0, S - 1, 0, S - 1, FORCE>(ax, ay, az, fx, fy, fz, nx, ny, nz, e6, en3, rx, ry, rz);
+        if (FORCE) { PITA_UNPACK_R(); put(3, half_atom(1), xl, yl, zl); put(3, half_atom(2), xh, yh, zh); }
+        lj_block_step<S, 0, S - 1, 1, 0, FORCE>(ax, ay, az, fx, fy, fz, bx, by, bz, e6, en3, rx, ry, rz);
+        if (FORCE) { PITA_UNPACK_R(); put(3, half_atom(3), xl, yl, zl); }
+      } else {           // own atoms 4..6 against all seven atoms of group g-4
+        load2(half_atom(0), half_atom(1), bx, by, bz);
+        load2(half_atom(2), half_atom(3), nx, ny, nz);
+        lj_block_step<S, 4, 6, 4, 6, FORCE>(ax, ay, az, fx, fy, fz, bx, by, bz, e6, en3, rx, ry, rz);
+        load2(half_atom(4), half_atom(5), bx, by, bz);
+        if (FORCE) { PITA_UNPACK_R(); put(3, half_atom(0), xl, yl, zl); put(3, half_atom(1), xh, yh, zh); }
+        lj_block_step<S, 4, 6, 4, 6, FORCE>(ax, ay, az, fx, fy, fz, nx, ny, nz, e6, en3, rx, ry, rz);
+        load2(half_atom(6), rect_atom(20), nx, ny, nz);
+        if (FORCE) { PITA_UNPACK_R(); put(3, half_atom(2), xl, yl, zl); put(3, half_atom(3), xh, yh, zh); }
+        lj_block_step<S, 4, 6, 4, 6, FORCE>(ax, ay, az, fx, fy, fz, bx, by, bz, e6, en3, rx, ry, rz);
+        if (FORCE) { PITA_UNPACK_R(); put(3, half_atom(4), xl, yl, zl); put(3, half_atom(5), xh, yh, zh); }
+        lj_block_step<S, 4, 6, 0, S - 1, FORCE>(ax, ay, az, fx, fy, fz, nx, ny, nz, e6, en3, rx, ry, rz);
+        if (FORCE) { PITA_UNPACK_R(); put(3, half_atom(6), xl, yl, zl); put(2, rect_atom(20), xh, yh, zh); }
+      }
+    }
+#undef PITA_UNPACK_R
+    __syncthreads();
+
+    // Every streamed position was read before this barrier, so the position rows of this tile are free: they become the
+    // coalescing stage of the force rows.
+    if (active) {
+      float a_lo, a_hi, b_lo, b_hi;
+      unpk2(e6, a_lo, a_hi);
+      unpk2(en3, b_lo, b_hi);
+      const float e_pairs = (a_lo + a_hi) + 2.0f * (b_lo + b_hi);  // this thread's unordered pairs: sum r^-12 - 2 r^-6
+      float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg) {
+        const float4 q = s_part[gg * C::CPB + c];
+        cx += q.x; cy += q.y; cz += q.z;
+      }
+      cx *= (1.0f / NA); cy *= (1.0f / NA); cz *= (1.0f / NA);
+      const float k24 = 24.0f * energy_factor * inv_T, ko = osc * inv_T;
+      float e_osc = 0.f;
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        const bool real = (r < S - 1) || (g < G - 1);
+        const float ux = ax[r] - cx, uy = ay[r] - cy, uz = az[r] - cz;
+        if (real) e_osc = fmaf(ux, ux, fmaf(uy, uy, fmaf(uz, uz, e_osc)));
+        if (FORCE && real) {
+          float lo, hi, px, py, pz;
+          unpk2(fx[r], lo, hi); px = -(lo + hi);
+          unpk2(fy[r], lo, hi); py = -(lo + hi);
+          unpk2(fz[r], lo, hi); pz = -(lo + hi);
+          const float *sp = s_react + ((a0 + r) * 3) * C::CPB + c;
+#pragma unroll
+          for (int sl = 0; sl < C::kSlots; ++sl) {
+            // slots 0..2: written by threads g-1, g-2, g-3 for every atom; slot 3: by thread g+4 for every atom of groups
+            // 0-3, by thread g-4 for atoms 0..3 of groups 4-7
+            if (sl < 3 || r < 4 || g < G / 2) {
+              const float *q = sp + sl * NP * 3 * C::CPB;
+              px += q[0]; py += q[C::CPB]; pz += q[2 * C::CPB];
+            }
+          }
+          float *o = s_pos + c * P + 3 * (a0 + r);
+          o[0] = fmaf(k24, px, -ko * ux); o[1] = fmaf(k24, py, -ko * uy); o[2] = fmaf(k24, pz, -ko * uz);
+        }
+      }
+      s_en[g * C::CPB + c] = energy_factor * 2.0f * e_pairs + osc * 0.5f * e_osc;
+    }
+    __syncthreads();
+    if (g == 0 && active) {
+      float v = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg) v += s_en[gg * C::CPB + c];
+      logp[(int64_t)tile * C::CPB + c] = -v * inv_T;
+    }
+    if (FORCE) {
+      float *__restrict__ dst = force + (int64_t)tile * C::CPB * D;
+      const int nvec = nflt >> 2;
+      for (int v = tid; v < nvec; v += C::kThreads)
+        reinterpret_cast<float4 *>(dst)[v] = reinterpret_cast<const float4 *>(s_pos)[v];
+      for (int f = (nvec << 2) + tid; f < nflt; f += C::kThreads) dst[f] = s_pos[f];
+    }
+  }
+}
+
+#pragma nv_diag_default 549
+
+template <int NA>
+static int launch_lj_blocked(const float *x, int64_t B, float T, float ef, float osc, float *logp, float *force,
+                             cudaStream_t st) {
+  using C = LJBlockCfg<NA>;
+  const int64_t blocks = (B + C::CPB - 1) / C::CPB;
+  PITA_REQUIRE(blocks < (1ll << 31), PITA_EINVAL, "lj: batch too large");
+  cudaFuncSetAttribute(lj_blocked_kernel<NA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  cudaFuncSetAttribute(lj_blocked_kernel<NA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  if (force != nullptr)
+    lj_blocked_kernel<NA, true><<<(unsigned)blocks, C::kThreads, C::kSmemBytes, st>>>(x, B, 1.0f / T, ef, osc, logp, force);
+  else
+    lj_blocked_kernel<NA, false><<<(unsigned)blocks, C::kThreads, C::kSmemBytes, st>>>(x, B, 1.0f / T, ef, osc, logp, force);
+  PITA_CHECK_LAUNCH("lj_blocked_kernel");
+  return PITA_OK;
+}
+
 template <int NA, int G, int CW, int MINB>
 static int launch_lj_pairs(const float *x, int64_t B, float T, float ef, float osc, float *logp, float *force,
                            cudaStream_t st) {
@@ -438,8 +712,9 @@ extern "C" int pita_lj_energy_force(const float *x, int64_t B, int n, float temp
         if (cfg == 2) return launch_lj_pairs<55, 11, 1, 4>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
         if (cfg == 3) return launch_lj_pairs<55, 11, 1, 2>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
         if (cfg == 4) return launch_lj_pairs<55, 5, 2, 1>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+        if (cfg == 8) return launch_lj_pairs<55, 5, 1, 2>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
       }
-      return launch_lj_pairs<55, 5, 1, 2>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
+      return launch_lj_blocked<55>(x, B, temperature, energy_factor, oscillator_scale, logp, force, st);
     default:
       set_error("lj: n_particles=%d unsupported (reference raises NotImplementedError for n not in {13,55}, "
                 "lennardjones_energy.py:177-178)", n);

@@ -12,8 +12,12 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 import functools
+import os
 
 from . import _native as N
+
+
+NVTX = os.environ.get("PITA_NVTX", "0") not in ("", "0")
 
 
 def _on_device(fn):
@@ -26,7 +30,13 @@ def _on_device(fn):
         if dev is None:
             return fn(*args, **kwargs)
         with torch.cuda.device(dev):
-            return fn(*args, **kwargs)
+            if not NVTX:
+                return fn(*args, **kwargs)
+            torch.cuda.nvtx.range_push("pita." + fn.__name__)  # PITA_NVTX=1: one range per native call (ncu --nvtx / nsys)
+            try:
+                return fn(*args, **kwargs)
+            finally:
+                torch.cuda.nvtx.range_pop()
 
     return wrapped
 

@@ -338,3 +338,67 @@ def test_prior_sample():
     assert_close(lp, ref, "log_prob", rtol=1e-5)
     free = Prior(scale, n_particles=n, spatial_dim=3, device="cuda", should_mean_free=False)
     assert free.sample(5).shape == (5, 3 * n)
+
+
+def test_generate_samples_with_the_real_integrator():
+    """SURVEY §8f-2 on the GPU: `generate_samples` (energytemp_module.py:237-298) driving the real prior and the real
+    integrator: the first pass resamples, the second (log-weight) pass runs the first `inference_batch_size` prior samples with
+    resampling off.  Both passes are replayed through the fp64 oracle from the SAME prior samples / noise / offsets."""
+    from functools import partial
+
+    from pita_b200.annealing_factor_schedules import ConstantAnnealingFactorSchedule
+    from pita_b200.base_prior import Prior
+    from pita_b200.lennardjones_energy import LennardJonesEnergy
+    from pita_b200.noise_schedules import ElucidatingNoiseSchedule
+    from pita_b200.sampling import generate_samples
+    n, N, S, chunk, time_range, gam, beta = 13, 72, 6, 24, 0.2, 4.0 / 3.0, 0.9
+    sdE = O.random_egnn_state(seed=71, dtype=torch.float64, coord_gain=0.3)
+    sdS = O.random_egnn_state(seed=72, dtype=torch.float64, coord_gain=0.3)
+    gen = torch.Generator().manual_seed(5)
+    noise = {s: torch.randn(N, 3 * n, generator=gen, dtype=torch.float64) for s in range(S)}
+    u0 = {s: float(torch.rand(1, generator=gen, dtype=torch.float64)) for s in range(S + 1)}
+    integ = _build_integrator(n, sdE, sdS, S, chunk, start_resampling_step=0, end_resampling_step=10 ** 9, resampling_interval=1,
+                              time_range=time_range)
+    integ.noise_fn = lambda step, x: noise[step][: x.shape[0]].float().cuda()
+    integ.u0_fn = lambda step: u0[step]
+    drawn = []
+
+    def recording_prior(scale, device):
+        pr = Prior(scale, n_particles=n, spatial_dim=3, device=device)
+        sample = pr.sample
+        pr.sample = lambda k: drawn.append(sample(k)) or drawn[-1]
+        return pr
+
+    sched = ElucidatingNoiseSchedule(0.05, 80.0, 7.0)
+    torch.manual_seed(11)
+    out = generate_samples(weighted_sde_integrator=integ, energy_function=LennardJonesEnergy(dimensionality=3 * n, n_particles=n),
+                           num_samples=N, noise_schedule=sched, annealing_factor_schedule=partial(ConstantAnnealingFactorSchedule),
+                           partial_prior=recording_prior, t_start=torch.tensor(time_range), device="cuda", inference_batch_size=chunk,
+                           num_integration_steps=S, inverse_temp=beta, annealing_factor=gam, return_logweights=True)
+    samples, not_resampled, logw, uniq, terms, acc = out
+    assert len(drawn) == 1 and drawn[0].shape == (N, 3 * n)
+    x1 = drawn[0].double().cpu()
+    # the prior really has the reference's scale sqrt(h(t_start) / gamma)
+    osched = O.EDMSchedule(0.05)
+    scale = float((osched.h(torch.tensor(time_range, dtype=torch.float64)) / gam) ** 0.5)
+    assert abs(float(x1.std()) / (scale * (1 - 1 / n) ** 0.5) - 1.0) < 0.1
+    assert samples.shape == (N, 3 * n) and not_resampled.shape == (chunk, 3 * n) and logw.shape[1] == chunk
+
+    def replay(x_start, interval):
+        cursor = {}
+
+        def noise_fn(step, xc):
+            lo = cursor.get(step, 0)
+            cursor[step] = lo + xc.shape[0]
+            return noise[step][lo:lo + xc.shape[0]]
+
+        cfg = O.LoopConfig(n=n, steps=S, chunk=chunk, beta=beta, resampling_interval=interval, time_range=time_range)
+        return O.integrate(sdE, sdS, osched, O.ConstGamma(gam), cfg, x_start, noise_fn, lambda s: u0[s])
+
+    x_ref, _, uniq_ref = replay(x1, 1)
+    assert list(uniq) == list(uniq_ref) and min(uniq) < N
+    assert_close(samples, x_ref, "generate_samples: resampled pass", rtol=1e-3)
+    x_nr, logw_nr, uniq_nr = replay(x1[:chunk], S + 1)
+    assert list(uniq_nr) == [chunk] * S
+    assert_close(not_resampled, x_nr, "generate_samples: log-weight pass particles", rtol=1e-3)
+    assert_close(logw, logw_nr, "generate_samples: log-weights", rtol=1e-3)
