@@ -64,6 +64,13 @@ int pita_egnn_forward(const float *wpack, int hidden, int layers, int n, const f
 int pita_egnn_energy(const float *wpack, int hidden, int layers, int n, const float *ht, const float *x,
                      const float *beta, int64_t B, float *energy, float *grad_x, float *dE_dh, void *stream);
 
+/* compute_laplacian_exact of EnergyNet.forward_energy (models/components/utils.py:68-77, called from sdes.py:204-216
+ * when the SDE has no score net): laplacian[B] = tr(Hess_x E)(ht[B], x[B][3n], beta[B]), pin=False, without the
+ * precondition_beta factor (the host wrapper applies it).  Exact (second-order forward Taylor mode, fp32); built for
+ * hidden=32, layers=3, n in {13, 55}; returns PITA_EUNSUP otherwise. */
+int pita_egnn_energy_laplacian(const float *wpack, int hidden, int layers, int n, const float *ht, const float *x,
+                               const float *beta, int64_t B, float *laplacian, void *stream);
+
 /* ScoreNet.forward (models/components/score_net.py:13-43) and the exact divergence
  * tr(d score / d x) of compute_divergence_exact (models/components/utils.py:43-51):
  * score[B][3n], div[B] (NULL to skip the divergence).

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpita_b200.so")
-SOURCES = ["capi.cu", "lj.cu", "resample.cu", "sde.cu", "egnn.cu", "egnn_rows.cu", "egnn_tri_a.cu", "egnn_tri_b.cu", "egnn_ad2.cu",
+SOURCES = ["capi.cu", "lj.cu", "resample.cu", "sde.cu", "egnn.cu", "egnn_rows.cu", "egnn_tri_a.cu", "egnn_tri_b.cu", "egnn_ad2.cu", "egnn_lap.cu",
            "umma_selftest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -93,6 +93,7 @@ SIGNATURES = {
     "pita_egnn_pack_floats": (_I64, [_I, _I]),
     "pita_egnn_forward": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P]),
     "pita_egnn_energy": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "pita_egnn_energy_laplacian": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P]),
     "pita_egnn_score_div_workspace_bytes": (_I64, [_I, _I]),
     "pita_egnn_tri_workspace_layout": (_I64, [_I, ctypes.POINTER(_I64), _I]),
     "pita_egnn_score_div": (_I, [_P, _I, _I, _I, _P, _P, _P, _I64, _P, _P, _I, _P, _I64, _P]),

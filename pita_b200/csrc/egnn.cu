@@ -689,6 +689,9 @@ int tri_particles_per_cta_a(int n);
 int64_t workspace_floats_per_particle(int n);
 int64_t workspace_layout(int n, int64_t *out, int max_out);
 }  // namespace tri
+namespace lap {
+int launch_laplacian(int n, const float *w, const float *ht, const float *x, const float *beta, int64_t B, float *lap, cudaStream_t s);
+}  // namespace lap
 namespace ad2 {
 int64_t pack_floats();
 int launch_forward(const float *w, const float *tc, const float *y, const float *beta, int64_t B, float *vel, cudaStream_t s);
@@ -737,6 +740,20 @@ extern "C" int pita_egnn_energy(const float *wpack, int hidden, int layers, int 
 
 // particles per (phase A, phase B) launch pair of the bilinear engine: one full wave of phase-A CTAs
 static int64_t tri_batch(int n) { return (int64_t)kNumSMs * tri::tri_particles_per_cta_a(n); }
+
+extern "C" int pita_egnn_energy_laplacian(const float *wpack, int hidden, int layers, int n, const float *ht, const float *x,
+                                          const float *beta, int64_t B, float *laplacian, void *stream) {
+  int rc = check_common("egnn_energy_laplacian", wpack, hidden, layers, n, ht, x, beta, B);
+  if (rc) return rc;
+  if (B == 0) return PITA_OK;
+  PITA_REQUIRE(laplacian, PITA_EINVAL, "egnn_energy_laplacian: null output");
+  if (is_ad2(hidden, layers, n)) {
+    set_error("egnn_energy_laplacian: built for the LJ networks (hidden 32, 3 layers, n = 13 / 55); the 22-atom configuration of "
+              "the reference always carries a score net");
+    return PITA_EUNSUP;
+  }
+  return lap::launch_laplacian(n, wpack, ht, x, beta, B, laplacian, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int64_t pita_egnn_score_div_workspace_bytes(int n, int mode) {
   if (mode == PITA_DIV_FP32 || n == 22) return 0;  // (the 22-atom network runs on the CUDA cores: no workspace)

@@ -46,6 +46,18 @@ class EnergyNet(nn.Module):
             e = w * u0 + (1 - w) * e
         return e, g, de_dt
 
+    def laplacian(self, ht, xt, beta, pin=False, t=None):
+        """tr(Hess_x forward_energy) — what the reference obtains from compute_laplacian_exact(partial(forward_energy, ...))
+        (sdes.py:204-216).  The pinned target is detached in the reference, so only the (1 - (1-t)^3) E part contributes."""
+        net = self.net
+        lap = ops.egnn_energy_laplacian(net.packed_weights(xt.device), net.hidden_nf, net.n_layers, net._n_particles, ht, xt, beta)
+        if self.precondition_beta:
+            lap = lap * ops._expand(beta, xt.shape[0], xt.device)
+        if pin:
+            assert t is not None
+            lap = (1 - (1 - t) ** 3) * lap
+        return lap
+
     def forward_energy(self, ht, xt, beta, pin=False, energy_function=None, t=None):
         e, _, _ = self._terms(ht, xt, beta, False, False)
         if pin:

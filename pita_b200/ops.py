@@ -101,6 +101,19 @@ DIV_MODES = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bilinear": 3}
 _div_ws = {}
 
 
+@_on_device
+def egnn_energy_laplacian(wpack, hidden, layers, n, ht, x, beta) -> torch.Tensor:
+    """tr(Hess_x E) per particle (compute_laplacian_exact of EnergyNet.forward_energy, utils.py:68-77)."""
+    lib = N.load()
+    x = N.as_f32(x)
+    B = x.shape[0]
+    ht, beta = _expand(ht, B, x.device), _expand(beta, B, x.device)
+    lap = torch.empty(B, device=x.device, dtype=torch.float32)
+    N.check(lib.pita_egnn_energy_laplacian(N.ptr(wpack), hidden, layers, n, N.ptr(ht), N.ptr(x), N.ptr(beta), B, N.ptr(lap),
+                                           N.stream_ptr(x.device)), "pita_egnn_energy_laplacian")
+    return lap
+
+
 def default_div_mode() -> str:
     """PITA_DIV_MODE=bilinear|3xtf32|tf32|fp32.  Default: bilinear — the round-2 engine (csrc/egnn_tri_*.cu, one dense product
     per (middle-layer edge, tangent node)); 3xtf32 / tf32 are the round-1 forward-mode kernel, fp32 the CUDA-core one."""

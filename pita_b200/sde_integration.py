@@ -251,7 +251,13 @@ class WeightedSDEIntegrator:
                                         remove_mean=self.should_mean_free, want_a_raw=False)
             return x_next, torch.zeros_like(a), B * self._world()[0], None
         ht = torch.full((B,), sc["h"], device=x.device, dtype=torch.float32)
-        score, div = self.sde.score_net.score_and_divergence(ht, x, beta, need_div=debias)
+        no_score_net = self.sde.score_net is None   # the Laplacian branch (reference sdes.py:169-170, 204-216)
+        if no_score_net:
+            if not debias:
+                raise AssertionError("f_not_debiased needs a score net (reference sdes.py:118)")
+            score = div = None
+        else:
+            score, div = self.sde.score_net.score_and_divergence(ht, x, beta, need_div=debias)
         if debias:
             if self.sde.pin_energy:
                 tt = torch.full((B,), t32, device=x.device, dtype=torch.float32)
@@ -261,6 +267,10 @@ class WeightedSDEIntegrator:
             else:
                 U, grad_u, dE_dh = self.sde.energy_net._terms(ht, x, beta, True, True)
                 dh_dt = sc["dh_dt"]
+            if no_score_net:  # b = -grad U g^2/2 and div b = -laplacian(U) g^2/2: the fused step sees them as its score / div
+                score = -grad_u
+                tt = torch.full((B,), t32, device=x.device, dtype=torch.float32) if self.sde.pin_energy else None
+                div = -self.sde.energy_net.laplacian(ht, x, beta, pin=self.sde.pin_energy, t=tt)
         else:
             U = grad_u = dE_dh = None
             dh_dt = 0.0

@@ -82,16 +82,18 @@ class VEReverseSDE:
         if not self.debias_inference:
             return self.f_not_debiased(t, x, beta, gamma)
         assert self.energy_net is not None
-        if self.score_net is None:
-            raise NotImplementedError("the Laplacian branch (score_net=None, sdes.py:204-216) is not built")
         ht = self.noise_schedule.h(t)
         g2 = self.g(t).pow(2)
         U, nabla_U, dU_dt = self.energy_net.energy_grad_dh(ht, x, beta, pin=self.pin_energy, energy_function=energy_function,
                                                            t=t, dh_dt=self.dh_dt(t))
-        s_t, div_s = self.score_net.score_and_divergence(ht, x, beta)
-        bt = s_t * g2[:, None] / 2
+        if self.score_net is not None:
+            s_t, div_s = self.score_net.score_and_divergence(ht, x, beta)
+            bt = s_t * g2[:, None] / 2
+            div_bt = div_s * g2 / 2
+        else:  # no score net (sdes.py:169-170, 204-216): b = -grad U g^2/2, div b = -laplacian(U) g^2/2
+            bt = -nabla_U * g2[:, None] / 2
+            div_bt = -self.energy_net.laplacian(ht, x, beta, pin=self.pin_energy, t=t) * g2 / 2
         drift_X = gamma[:, None] * -nabla_U * g2[:, None] / 2 + gamma[:, None] * bt  # sdes.py:172-174 (gamma_score := gamma, :143)
-        div_bt = div_s * g2 / 2
         inner = (-nabla_U * bt).sum(-1)
         raw = gamma * gamma * inner + gamma * div_bt + gamma * dU_dt + gamma_energy_schedule.dgamma_dt(t).to(dev) * U
         # clamp at this call's own 0.9-quantile (sdes.py:230) — one chunk == one call

@@ -144,7 +144,7 @@ def test_ad2_egnn_oracle_vs_reference_golden(golden_dir):
 def test_laplacian_branch_oracle_vs_reference_golden(golden_dir):
     """VEReverseSDE.f without a score net (b = -grad U g^2/2, div b = -laplacian(U) g^2/2 through
     compute_laplacian_exact, sdes.py:150-153, 204-216).  Oracle vs the unmodified reference in fp64 (fixture:
-    oracle/make_golden.py laplacian).  The CUDA path raises NotImplementedError for this branch; this pins its oracle."""
+    oracle/make_golden.py laplacian).  Pins the oracle of csrc/egnn_lap.cu (tests/test_gpu_laplacian.py)."""
     g = _load(golden_dir, "fk_n13_laplacian.npz")
     n = int(g["n"])
     d = O.fk_drift(_sd(g, "E."), None, O.EDMSchedule(float(g["sigma_min"])), O.ConstGamma(float(g["gamma"])), float(g["t"]),
