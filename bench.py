@@ -416,6 +416,8 @@ def main():
     hx = torch.empty(N, D, pin_memory=True).copy_(torch.randn(N, D) * scale)
     hx_out = torch.empty(N, D).pin_memory()
     hlw = torch.empty(S_E2E, N).pin_memory()
+    # one untimed call first: it creates the integrator's resampler (with several ranks: the symmetric-memory rendezvous)
+    integ_e.integrate_sde(hx.to(dev, non_blocking=True), tgt, gam, inverse_temperature=BETA)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     KE = max(1, min(K, 2))

@@ -179,3 +179,36 @@ def test_generate_samples_call_contract():
     assert torch.equal(calls[1]["x1"], calls[0]["x1"][:4])     # the SAME prior samples, first inference_batch_size of them
     samples, not_resampled, logw, uniq, terms, acc = out
     assert samples.shape == (10, 6) and not_resampled.shape == (4, 6) and logw.shape == (5, 4) and uniq == [10] * 5
+
+
+def test_ad2_class_state_dict_matches_the_reference(golden_dir):
+    """EGNN_dynamics_AD2_cat (egnn_dynamics_ad2_cat.py:11-65) as a drop-in: same parameter names and shapes as the reference
+    module (read from the fixture the unmodified reference wrote), so reference checkpoints load; unsupported configurations
+    raise instead of falling back; the weight pack has the size the C ABI states."""
+    import numpy as np
+
+    from pita_b200 import ops
+    from pita_b200.egnn_dynamics_ad2_cat import EGNN_dynamics_AD2_cat, atom_types_ad2, pack_state_dict_ad2
+    g = np.load(os.path.join(golden_dir, "egnn_ad2_n22.npz"))
+    ref = {k[2:]: g[k].shape for k in g.files if k.startswith("W.")}
+    net = EGNN_dynamics_AD2_cat(n_particles=22, n_dimensions=3, hidden_nf=64, n_layers=5, act_fn=torch.nn.SiLU(), recurrent=True,
+                                attention=True, tanh=True, agg="sum", condition_beta=True)
+    mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert mine == {k: tuple(s) for k, s in ref.items()}
+    assert list(net.state_dict().keys()) == [k[2:] for k in g.files if k.startswith("W.")]  # creation order too
+    net.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("W.")})
+    t = atom_types_ad2(22)
+    assert t.max().item() == 20 and torch.nn.functional.one_hot(t).shape == (22, 21)
+    for bad in (dict(n_particles=21), dict(hidden_nf=32), dict(n_layers=4), dict(condition_beta=False), dict(agg="mean")):
+        kw = dict(n_particles=22, n_dimensions=3, hidden_nf=64, n_layers=5, condition_beta=True)
+        kw.update(bad)
+        with pytest.raises(NotImplementedError):
+            EGNN_dynamics_AD2_cat(**kw)
+    w = pack_state_dict_ad2(net.state_dict(), 64, 5, "cpu")
+    assert w.numel() == ops.egnn_pack_floats(64, 5) and w.dtype == torch.float32
+    # spot checks of the layout (csrc/egnn_ad2.cu, namespace ad2::pk): embedding stored [feature][64]; first block = A^T of layer 0
+    emb = net.state_dict()["egnn.embedding.weight"]
+    assert torch.equal(w[: 23 * 64].reshape(23, 64), emb.t())
+    A = net.state_dict()["egnn.gcl_0.edge_mlp.0.weight"][:, :64]
+    off = 23 * 64 + 64
+    assert torch.equal(w[off: off + 4096].reshape(64, 64), A.t())
