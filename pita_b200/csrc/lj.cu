@@ -214,7 +214,18 @@ lj_pairs_kernel(const float *__restrict__ x, int64_t B, float inv_T, float energ
 
   // ---- stage: straight float4 copy; a configuration's row pitch (3*NA floats) is odd, so lane = configuration
   //      makes every scalar LDS / STS below bank-conflict free
-  {
+  if (ncfg == C::CPB && (C::CPB * D) % 4 == 0) {
+    // full tile: every load is issued before the first store (the plain loop below waits for each load in turn: with a dozen
+    // iterations that latency was most of an LJ-13 CTA's life)
+    constexpr int NV = C::CPB * D / 4, PER = (NV + C::kThreads - 1) / C::kThreads;
+    float4 buf[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+      if (tid + k * C::kThreads < NV) buf[k] = __ldg(reinterpret_cast<const float4 *>(src) + tid + k * C::kThreads);
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+      if (tid + k * C::kThreads < NV) reinterpret_cast<float4 *>(s_pos)[tid + k * C::kThreads] = buf[k];
+  } else {
     const int nvec = nflt >> 2;
     for (int v = tid; v < nvec; v += C::kThreads)
       reinterpret_cast<float4 *>(s_pos)[v] = __ldg(reinterpret_cast<const float4 *>(src) + v);
