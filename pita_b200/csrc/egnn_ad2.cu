@@ -38,11 +38,36 @@ constexpr int A_f = 0, B_f = M, A_b = 2 * M, B_b = 3 * M, W2_f = 4 * M, W2_b = 5
 }  // namespace pk
 
 struct V2 {
-  float a, b;  // channels lane and lane + 32
+  float a, b;  // channels 2*lane and 2*lane + 1 (adjacent: one 64-bit shared-memory access, one packed FFMA2 per weight pair)
 };
-__device__ __forceinline__ V2 ld2(const float *p, int lane) { return V2{p[lane], p[lane + 32]}; }
-__device__ __forceinline__ void st2(float *p, int lane, V2 v) { p[lane] = v.a; p[lane + 32] = v.b; }
-__device__ __forceinline__ V2 ldg2(const float *__restrict__ p, int lane) { return V2{__ldg(p + lane), __ldg(p + lane + 32)}; }
+__device__ __forceinline__ V2 ld2(const float *p, int lane) {
+  const float2 v = *reinterpret_cast<const float2 *>(p + 2 * lane);
+  return V2{v.x, v.y};
+}
+__device__ __forceinline__ void st2(float *p, int lane, V2 v) { *reinterpret_cast<float2 *>(p + 2 * lane) = make_float2(v.a, v.b); }
+__device__ __forceinline__ V2 ldg2(const float *__restrict__ p, int lane) {
+  const float2 v = __ldg(reinterpret_cast<const float2 *>(p + 2 * lane));
+  return V2{v.x, v.y};
+}
+// packed fp32 pair (FFMA2: two FMAs per issue slot, the only way sm_100a reaches its FP32 rate -- profiles/ubench)
+struct P2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ P2 pk2(float lo, float hi) {
+  P2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ V2 unpk2(P2 a) {
+  V2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.a), "=f"(r.b) : "l"(a.v));
+  return r;
+}
+__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) {
+  P2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return d;
+}
 __device__ __forceinline__ float wsum2(V2 v) { return warp_sum(v.a + v.b); }
 
 // alanine dipeptide atom typing (egnn_dynamics_ad2_cat.py:67-73): one class per atom except three hydrogen triples
@@ -56,22 +81,28 @@ __device__ __forceinline__ int atom_type22(int i) {
 // out[t] = W v_t for NV vectors staged contiguously at vs (each H floats, 16-byte aligned); W: shared memory, layout [k][c]
 template <int NV>
 __device__ __forceinline__ void matvec(const float *W, const float *vs, int lane, V2 (&out)[NV]) {
+  P2 acc[NV];
 #pragma unroll
-  for (int t = 0; t < NV; ++t) out[t] = V2{0.f, 0.f};
+  for (int t = 0; t < NV; ++t) acc[t] = pk2(0.f, 0.f);
 #pragma unroll 4
   for (int k4 = 0; k4 < H / 4; ++k4) {
     float4 v[NV];
 #pragma unroll
     for (int t = 0; t < NV; ++t) v[t] = *reinterpret_cast<const float4 *>(vs + t * H + 4 * k4);
-    const float *w = W + (4 * k4) * H + lane;
-    const float w0a = w[0], w0b = w[32], w1a = w[H], w1b = w[H + 32], w2a = w[2 * H], w2b = w[2 * H + 32], w3a = w[3 * H],
-                w3b = w[3 * H + 32];
+    const float *w = W + (4 * k4) * H + 2 * lane;
+    const float2 w0 = *reinterpret_cast<const float2 *>(w), w1 = *reinterpret_cast<const float2 *>(w + H),
+                 w2 = *reinterpret_cast<const float2 *>(w + 2 * H), w3 = *reinterpret_cast<const float2 *>(w + 3 * H);
+    const P2 p0 = pk2(w0.x, w0.y), p1 = pk2(w1.x, w1.y), p2 = pk2(w2.x, w2.y), p3 = pk2(w3.x, w3.y);
 #pragma unroll
     for (int t = 0; t < NV; ++t) {
-      out[t].a = fmaf(w0a, v[t].x, fmaf(w1a, v[t].y, fmaf(w2a, v[t].z, fmaf(w3a, v[t].w, out[t].a))));
-      out[t].b = fmaf(w0b, v[t].x, fmaf(w1b, v[t].y, fmaf(w2b, v[t].z, fmaf(w3b, v[t].w, out[t].b))));
+      acc[t] = fma2(p0, pk2(v[t].x, v[t].x), acc[t]);
+      acc[t] = fma2(p1, pk2(v[t].y, v[t].y), acc[t]);
+      acc[t] = fma2(p2, pk2(v[t].z, v[t].z), acc[t]);
+      acc[t] = fma2(p3, pk2(v[t].w, v[t].w), acc[t]);
     }
   }
+#pragma unroll
+  for (int t = 0; t < NV; ++t) out[t] = unpk2(acc[t]);
 }
 
 // cooperative copy of `count` H x H matrices from the packed buffer into shared-memory slots (all threads call)
@@ -123,12 +154,14 @@ struct EdgeP {
   float th, phi;  // tanh(u), phi = tanh(u) * range
 };
 
-// per-warp staging: primal [2][H] then tangents [2][TTMAX][H]
+// per-warp staging: two groups of [primal][TTMAX tangents] x H, each group contiguous so that ONE pass over a weight matrix
+// serves the primal vector and its tangents (the kernels are bound by shared-memory bandwidth: ncu r2aa, 74 % of the peak
+// wavefront rate at 29 % FMA-pipe occupancy; a weight row streamed from shared memory must feed as many FMAs as possible)
 template <int TTMAX>
 struct Stage {
   static constexpr int kFloats = 2 * H + 2 * TTMAX * H;
   float *pa, *pb, *ta, *tb;
-  __device__ __forceinline__ Stage(float *base) : pa(base), pb(base + H), ta(base + 2 * H), tb(base + 2 * H + TTMAX * H) {}
+  __device__ __forceinline__ Stage(float *base) : pa(base), pb(base + (1 + TTMAX) * H), ta(base + H), tb(base + (2 + TTMAX) * H) {}
 };
 
 template <int TT>
@@ -163,28 +196,26 @@ __device__ __forceinline__ EdgeP edge_eval(const float *sW2, const float *sWc1, 
                                e.f1.b * (tin.dpq[t].b + sc.c1.b * r2t + sc.d1.b * tin.dea[t])});
   }
   __syncwarp();
-  V2 o1[1];
-  matvec<1>(sW2, st.pa, lane, o1);
-  const V2 z2 = {sc.b2.a + o1[0].a, sc.b2.b + o1[0].b};
+  V2 o[1 + TT];
+  matvec<1 + TT>(sW2, st.pa, lane, o);   // [a1, tangents of a1]: one pass over W2
+  const V2 z2 = {sc.b2.a + o[0].a, sc.b2.b + o[0].b};
   e.m = silu_both2(z2, e.f2);
   e.s = sigmoidf_fast(wsum2(V2{sc.wa.a * e.m.a, sc.wa.b * e.m.b}) + sc.ba);
   e.ms = V2{e.m.a * e.s, e.m.b * e.s};
   st2(st.pb, lane, e.ms);
   if (TT > 0) {
     const float s1s = e.s * (1.0f - e.s);
-    V2 ot[TT > 0 ? TT : 1];
-    matvec<(TT > 0 ? TT : 1)>(sW2, st.ta, lane, ot);
 #pragma unroll
     for (int t = 0; t < TT; ++t) {
-      const V2 dm = {e.f2.a * ot[t].a, e.f2.b * ot[t].b};
+      const V2 dm = {e.f2.a * o[1 + t].a, e.f2.b * o[1 + t].b};
       const float ds = s1s * wsum2(V2{sc.wa.a * dm.a, sc.wa.b * dm.b});
       dms[t] = V2{dm.a * e.s + e.m.a * ds, dm.b * e.s + e.m.b * ds};
       st2(st.tb + t * H, lane, dms[t]);
     }
   }
   __syncwarp();
-  matvec<1>(sWc1, st.pb, lane, o1);
-  const V2 zc = {sc.bc1.a + o1[0].a, sc.bc1.b + o1[0].b};
+  matvec<1 + TT>(sWc1, st.pb, lane, o);  // [ms, tangents of ms]: one pass over Wc1
+  const V2 zc = {sc.bc1.a + o[0].a, sc.bc1.b + o[0].b};
   const V2 ac = silu_both2(zc, e.fc);
   const float u = wsum2(V2{sc.wc2.a * ac.a, sc.wc2.b * ac.b});
   e.th = tanhf(u);
@@ -193,11 +224,9 @@ __device__ __forceinline__ EdgeP edge_eval(const float *sW2, const float *sWc1, 
     const float dphi_du = rng * (1.0f - e.th * e.th);
     const V2 wfc = {sc.wc2.a * e.fc.a, sc.wc2.b * e.fc.b};
     const float k2 = g.inv * g.inv / g.nrm;
-    V2 ot[TT > 0 ? TT : 1];
-    matvec<(TT > 0 ? TT : 1)>(sWc1, st.tb, lane, ot);
 #pragma unroll
     for (int t = 0; t < TT; ++t) {
-      const float du = wsum2(V2{wfc.a * ot[t].a, wfc.b * ot[t].b});
+      const float du = wsum2(V2{wfc.a * o[1 + t].a, wfc.b * o[1 + t].b});
       const float dphi = dphi_du * du;
       const float c = dr2h[t] * k2;
 #pragma unroll
@@ -206,6 +235,78 @@ __device__ __forceinline__ EdgeP edge_eval(const float *sW2, const float *sWc1, 
   }
   __syncwarp();
   return e;
+}
+
+// EB edges of one receiver at once (tangent passes): the EB x (1 + TT) staged vectors share ONE pass over W2 and ONE over
+// Wc1, so every weight pair read from shared memory feeds EB x (1 + TT) packed FMAs.  The second group of vectors reuses the
+// staging rows of the first (a __syncwarp() separates the reads of one from the writes of the other).
+template <int TT, int EB>
+__device__ __forceinline__ void edge_eval_multi(const float *sW2, const float *sWc1, const EdgeScal &sc, float rng,
+                                                const V2 (&ppq)[EB], const EdgeGeo (&g)[EB], float *stg, int lane,
+                                                const EdgeT<TT> (&tin)[EB], V2 (&dms)[EB][TT], float (&dtr)[EB][TT][3]) {
+  constexpr int NV = EB * (1 + TT);
+  float dr2h[EB][TT];
+#pragma unroll
+  for (int e = 0; e < EB; ++e) {
+    const V2 z1 = {ppq[e].a + sc.c1.a * g[e].r2 + sc.d1.a * g[e].ea, ppq[e].b + sc.c1.b * g[e].r2 + sc.d1.b * g[e].ea};
+    V2 f1;
+    const V2 a1 = silu_both2(z1, f1);
+    st2(stg + (e * (1 + TT)) * H, lane, a1);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      dr2h[e][t] = g[e].d[0] * tin[e].Dd[t][0] + g[e].d[1] * tin[e].Dd[t][1] + g[e].d[2] * tin[e].Dd[t][2];
+      const float r2t = 2.0f * dr2h[e][t];
+      st2(stg + (e * (1 + TT) + 1 + t) * H, lane,
+          V2{f1.a * (tin[e].dpq[t].a + sc.c1.a * r2t + sc.d1.a * tin[e].dea[t]),
+             f1.b * (tin[e].dpq[t].b + sc.c1.b * r2t + sc.d1.b * tin[e].dea[t])});
+    }
+  }
+  __syncwarp();
+  V2 o[NV];
+  matvec<NV>(sW2, stg, lane, o);
+  __syncwarp();   // every lane has read the first group
+  float phi_s[EB];
+#pragma unroll
+  for (int e = 0; e < EB; ++e) {
+    const V2 z2 = {sc.b2.a + o[e * (1 + TT)].a, sc.b2.b + o[e * (1 + TT)].b};
+    V2 f2;
+    const V2 m = silu_both2(z2, f2);
+    const float sg = sigmoidf_fast(wsum2(V2{sc.wa.a * m.a, sc.wa.b * m.b}) + sc.ba);
+    st2(stg + (e * (1 + TT)) * H, lane, V2{m.a * sg, m.b * sg});
+    const float s1s = sg * (1.0f - sg);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      const V2 dm = {f2.a * o[e * (1 + TT) + 1 + t].a, f2.b * o[e * (1 + TT) + 1 + t].b};
+      const float ds = s1s * wsum2(V2{sc.wa.a * dm.a, sc.wa.b * dm.b});
+      dms[e][t] = V2{dm.a * sg + m.a * ds, dm.b * sg + m.b * ds};
+      st2(stg + (e * (1 + TT) + 1 + t) * H, lane, dms[e][t]);
+    }
+    phi_s[e] = 0.f;
+  }
+  __syncwarp();
+  matvec<NV>(sWc1, stg, lane, o);
+#pragma unroll
+  for (int e = 0; e < EB; ++e) {
+    const V2 zc = {sc.bc1.a + o[e * (1 + TT)].a, sc.bc1.b + o[e * (1 + TT)].b};
+    V2 fc;
+    const V2 ac = silu_both2(zc, fc);
+    const float u = wsum2(V2{sc.wc2.a * ac.a, sc.wc2.b * ac.b});
+    const float th = tanhf(u);
+    phi_s[e] = th * rng;
+    const float dphi_du = rng * (1.0f - th * th);
+    const V2 wfc = {sc.wc2.a * fc.a, sc.wc2.b * fc.b};
+    const float k2 = g[e].inv * g[e].inv / g[e].nrm;
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      const float du = wsum2(V2{wfc.a * o[e * (1 + TT) + 1 + t].a, wfc.b * o[e * (1 + TT) + 1 + t].b});
+      const float dphi = dphi_du * du;
+      const float c = dr2h[e][t] * k2;
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        dtr[e][t][b] = (tin[e].Dd[t][b] * g[e].inv - g[e].d[b] * c) * phi_s[e] + g[e].d[b] * g[e].inv * dphi;
+    }
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -514,8 +615,8 @@ ad2_energy_kernel(const float *__restrict__ wpack, const float *__restrict__ ht,
             matvec<1>(sW + 2 * pk::M, st.pb, lane, o);
             const V2 gz1 = {o[0].a * e.f1.a, o[0].b * e.f1.b};
             gp.a += gz1.a; gp.b += gz1.b;
-            gqw[j * H + lane] += gz1.a;
-            gqw[j * H + lane + 32] += gz1.b;
+            gqw[j * H + 2 * lane] += gz1.a;
+            gqw[j * H + 2 * lane + 1] += gz1.b;
             const float gr2 = wsum2(V2{sc.c1.a * gz1.a, sc.c1.b * gz1.b});
             const float gea = wsum2(V2{sc.d1.a * gz1.a, sc.d1.b * gz1.b});
             const float gd_dot = (gxo.x * g.d[0] + gxo.y * g.d[1] + gxo.z * g.d[2]) * e.phi;
@@ -548,7 +649,7 @@ ad2_energy_kernel(const float *__restrict__ wpack, const float *__restrict__ ht,
         for (int i = warp; i < NP; i += NW) {
           V2 gq = {0.f, 0.f};
 #pragma unroll 1
-          for (int w = 0; w < NW; ++w) { gq.a += sGQw[(w * NP + i) * H + lane]; gq.b += sGQw[(w * NP + i) * H + lane + 32]; }
+          for (int w = 0; w < NW; ++w) { gq.a += sGQw[(w * NP + i) * H + 2 * lane]; gq.b += sGQw[(w * NP + i) * H + 2 * lane + 1]; }
           __syncwarp();
           st2(sGAgg + i * H, lane, gq);  // stage (gagg is dead after the edge pass)
           __syncwarp();
@@ -729,14 +830,12 @@ ad2_score_div_kernel(const float *__restrict__ wpack, const float *__restrict__ 
             }
             const float4 xi = sX[l * NP + i], x0i = sX[i];
             const V2 pi = ld2(sP + i * H, lane);
-#pragma unroll 1
-            for (int j = 0; j < NP; ++j) {
-              if (j == i) continue;
-              if (first && i != k && j != k) continue;  // layer 0: only edges incident to the tangent node
+            // one edge's inputs: geometry, p_i + q_j, tangent bundle
+            auto prep = [&](int j, EdgeGeo &g, V2 &ppq, EdgeT<T> &tin) {
               const float4 x0j = sX[j];
-              const EdgeGeo g = edge_geo(xi, sX[l * NP + j], x0i, x0j);
+              g = edge_geo(xi, sX[l * NP + j], x0i, x0j);
               const V2 qj = ld2(sQ + j * H, lane);
-              EdgeT<T> tin;
+              ppq = V2{pi.a + qj.a, pi.b + qj.b};
               const float e0[3] = {x0i.x - x0j.x, x0i.y - x0j.y, x0i.z - x0j.z};
               const float sgn = (i == k) ? 1.0f : ((j == k) ? -1.0f : 0.0f);
 #pragma unroll
@@ -752,13 +851,42 @@ ad2_score_div_kernel(const float *__restrict__ wpack, const float *__restrict__ 
                 }
                 tin.dea[t] = 2.0f * sgn * e0[t];  // d edge_attr: only edges incident to the tangent node
               }
-              V2 dms[T];
-              float dtr[T][3];
-              edge_eval<T, T>(sW + 2 * pk::M, sW + 3 * pk::M, sc, rng, V2{pi.a + qj.a, pi.b + qj.b}, g, st, lane, tin, dms, dtr);
+            };
+            int jp = -1;   // a sender waiting for its partner
+#pragma unroll 1
+            for (int j = 0; j <= NP; ++j) {
+              if (j < NP) {
+                if (j == i) continue;
+                if (first && i != k && j != k) continue;  // layer 0: only edges incident to the tangent node
+                if (jp < 0) { jp = j; continue; }
+                EdgeGeo g2[2];
+                V2 ppq2[2];
+                EdgeT<T> tin2[2];
+                prep(jp, g2[0], ppq2[0], tin2[0]);
+                prep(j, g2[1], ppq2[1], tin2[1]);
+                jp = -1;
+                V2 dms2[2][T];
+                float dtr2[2][T][3];
+                edge_eval_multi<T, 2>(sW + 2 * pk::M, sW + 3 * pk::M, sc, rng, ppq2, g2, st.pa, lane, tin2, dms2, dtr2);
 #pragma unroll
-              for (int t = 0; t < T; ++t) {
-                dagg[t].a += dms[t].a; dagg[t].b += dms[t].b;
-                dxo[t][0] += dtr[t][0]; dxo[t][1] += dtr[t][1]; dxo[t][2] += dtr[t][2];
+                for (int t = 0; t < T; ++t) {
+                  dagg[t].a += dms2[0][t].a + dms2[1][t].a; dagg[t].b += dms2[0][t].b + dms2[1][t].b;
+                  dxo[t][0] += dtr2[0][t][0] + dtr2[1][t][0]; dxo[t][1] += dtr2[0][t][1] + dtr2[1][t][1];
+                  dxo[t][2] += dtr2[0][t][2] + dtr2[1][t][2];
+                }
+              } else if (jp >= 0) {   // odd sender left over
+                EdgeGeo g1[1];
+                V2 ppq1[1];
+                EdgeT<T> tin1[1];
+                prep(jp, g1[0], ppq1[0], tin1[0]);
+                V2 dms1[1][T];
+                float dtr1[1][T][3];
+                edge_eval_multi<T, 1>(sW + 2 * pk::M, sW + 3 * pk::M, sc, rng, ppq1, g1, st.pa, lane, tin1, dms1, dtr1);
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                  dagg[t].a += dms1[0][t].a; dagg[t].b += dms1[0][t].b;
+                  dxo[t][0] += dtr1[0][t][0]; dxo[t][1] += dtr1[0][t][1]; dxo[t][2] += dtr1[0][t][2];
+                }
               }
             }
             if (lane < T) {
@@ -808,15 +936,11 @@ ad2_score_div_kernel(const float *__restrict__ wpack, const float *__restrict__ 
           matvec<T>(sW, sDH + k * T * H, lane, dp);
           const float4 xk = sX[l * NP + k], x0k = sX[k];
           const V2 pk_ = ld2(sP + k * H, lane);
-          for (int j = warp; j < NP; j += NW) {
-            if (j == k) {  // identity path x^L_k = x^{L-1}_k + ...
-              trace += dxin[k * T + 0].x + dxin[k * T + 1].y + dxin[k * T + 2].z;
-              continue;
-            }
+          auto prep_last = [&](int j, EdgeGeo &g, V2 &ppq, EdgeT<T> &tin) {
             const float4 x0j = sX[j];
-            const EdgeGeo g = edge_geo(xk, sX[l * NP + j], x0k, x0j);
+            g = edge_geo(xk, sX[l * NP + j], x0k, x0j);
             const V2 qj = ld2(sQ + j * H, lane);
-            EdgeT<T> tin;
+            ppq = V2{pk_.a + qj.a, pk_.b + qj.b};
             const float e0[3] = {x0k.x - x0j.x, x0k.y - x0j.y, x0k.z - x0j.z};
 #pragma unroll
             for (int t = 0; t < T; ++t) {
@@ -826,10 +950,37 @@ ad2_score_div_kernel(const float *__restrict__ wpack, const float *__restrict__ 
               tin.Dd[t][0] = qk.x - qq.x; tin.Dd[t][1] = qk.y - qq.y; tin.Dd[t][2] = qk.z - qq.z;
               tin.dea[t] = 2.0f * e0[t];
             }
-            V2 dms[T];
-            float dtr[T][3];
-            edge_eval<T, T>(sW + 2 * pk::M, sW + 3 * pk::M, sc, rng, V2{pk_.a + qj.a, pk_.b + qj.b}, g, st, lane, tin, dms, dtr);
-            trace += dtr[0][0] + dtr[1][1] + dtr[2][2];
+          };
+          int jp = -1;
+#pragma unroll 1
+          for (int j = warp; j < NP + NW; j += NW) {
+            if (j < NP) {
+              if (j == k) {  // identity path x^L_k = x^{L-1}_k + ...
+                trace += dxin[k * T + 0].x + dxin[k * T + 1].y + dxin[k * T + 2].z;
+                continue;
+              }
+              if (jp < 0) { jp = j; continue; }
+              EdgeGeo g2[2];
+              V2 ppq2[2];
+              EdgeT<T> tin2[2];
+              prep_last(jp, g2[0], ppq2[0], tin2[0]);
+              prep_last(j, g2[1], ppq2[1], tin2[1]);
+              jp = -1;
+              V2 dms2[2][T];
+              float dtr2[2][T][3];
+              edge_eval_multi<T, 2>(sW + 2 * pk::M, sW + 3 * pk::M, sc, rng, ppq2, g2, st.pa, lane, tin2, dms2, dtr2);
+              trace += (dtr2[0][0][0] + dtr2[0][1][1] + dtr2[0][2][2]) + (dtr2[1][0][0] + dtr2[1][1][1] + dtr2[1][2][2]);
+            } else if (jp >= 0) {
+              EdgeGeo g1[1];
+              V2 ppq1[1];
+              EdgeT<T> tin1[1];
+              prep_last(jp, g1[0], ppq1[0], tin1[0]);
+              jp = -1;
+              V2 dms1[1][T];
+              float dtr1[1][T][3];
+              edge_eval_multi<T, 1>(sW + 2 * pk::M, sW + 3 * pk::M, sc, rng, ppq1, g1, st.pa, lane, tin1, dms1, dtr1);
+              trace += dtr1[0][0][0] + dtr1[0][1][1] + dtr1[0][2][2];
+            }
           }
           __syncthreads();
         }
@@ -861,6 +1012,9 @@ static int set_smem(K kernel, size_t bytes, const char *name) {
 static inline unsigned grid_for(int64_t B) { return (unsigned)(B < kNumSMs ? B : kNumSMs); }
 
 constexpr int kNP = 22, kNW = 8, kL = 5;
+// score / divergence: 11 warps = two receivers per warp exactly (22 atoms); the kernel runs dependent FMA chains at two to
+// three warps per scheduler, so the extra warps pay (8 warps: three rounds of 8 + 8 + 6 receivers)
+constexpr int kNWd = 11;
 
 int64_t pack_floats() { return pk::kHeader + (int64_t)kL * pk::kLayer; }
 
@@ -887,12 +1041,12 @@ int launch_energy(const float *w, const float *ht, const float *x, const float *
 }
 int launch_score_div(const float *w, const float *ht, const float *x, const float *beta, int64_t B, float *sc, float *dv,
                      cudaStream_t s) {
-  using Dp = DPlan<kNP, kNW, kL>;
+  using Dp = DPlan<kNP, kNWd, kL>;
   const size_t bytes = Dp::kFloats * sizeof(float);
-  auto k = ad2_score_div_kernel<kNP, kNW, kL>;
+  auto k = ad2_score_div_kernel<kNP, kNWd, kL>;
   int rc = set_smem(k, bytes, "ad2_score_div_kernel");
   if (rc) return rc;
-  k<<<grid_for(B), kNW * 32, bytes, s>>>(w, ht, x, beta, B, sc, dv);
+  k<<<grid_for(B), kNWd * 32, bytes, s>>>(w, ht, x, beta, B, sc, dv);
   PITA_CHECK_LAUNCH("ad2_score_div_kernel");
   return PITA_OK;
 }
