@@ -330,12 +330,15 @@ struct Plan {
 template <int NP, int NW>
 __device__ __forceinline__ void node_products(float *sm_P, float *sm_Q, const float *sW_A, const float *sW_B, const float *sHin,
                                               V2 b1, int lane, int warp) {
-  for (int i = warp; i < NP; i += NW) {
-    V2 o[1];
-    matvec<1>(sW_A, sHin + i * H, lane, o);
+  static_assert(NP % 2 == 0, "two adjacent nodes per weight pass");
+  for (int i = 2 * warp; i < NP; i += 2 * NW) {
+    V2 o[2];
+    matvec<2>(sW_A, sHin + i * H, lane, o);
     st2(sm_P + i * H, lane, V2{b1.a + o[0].a, b1.b + o[0].b});
-    matvec<1>(sW_B, sHin + i * H, lane, o);
+    st2(sm_P + (i + 1) * H, lane, V2{b1.a + o[1].a, b1.b + o[1].b});
+    matvec<2>(sW_B, sHin + i * H, lane, o);
     st2(sm_Q + i * H, lane, o[0]);
+    st2(sm_Q + (i + 1) * H, lane, o[1]);
   }
 }
 
@@ -794,11 +797,11 @@ ad2_score_div_kernel(const float *__restrict__ wpack, const float *__restrict__ 
         }
         node_products<NP, NW>(sP, sQ, sW, sW + pk::M, hin, ldg2(Wl + pk::b1, lane), lane, warp);
         if (!first) {  // dQ_j[a] = B dh_j[a]
-          for (int j = warp; j < NP; j += NW) {
-            V2 o[T];
-            matvec<T>(sW + pk::M, sDH + j * T * H, lane, o);
+          for (int j = 2 * warp; j < NP; j += 2 * NW) {
+            V2 o[2 * T];
+            matvec<2 * T>(sW + pk::M, sDH + j * T * H, lane, o);
 #pragma unroll
-            for (int t = 0; t < T; ++t) st2(sDQ + (j * T + t) * H, lane, o[t]);
+            for (int t = 0; t < 2 * T; ++t) st2(sDQ + (j * T + t) * H, lane, o[t]);
           }
         }
         __syncthreads();
@@ -906,22 +909,25 @@ ad2_score_div_kernel(const float *__restrict__ wpack, const float *__restrict__ 
             g2.count = 3;
             load_mats(sW, g2, P::kThreads);
           }
-          for (int i = warp; i < NP; i += NW) {
-            V2 f3, dz3[T], o[T];
-            silu_both2(ld2(sZ3 + (l * NP + i) * H, lane), f3);
-            matvec<T>(sW + pk::M, sDAgg + i * T * H, lane, dz3);
+          static_assert(NP % 2 == 0, "node-level passes take two adjacent nodes (2 x T contiguous rows) per weight pass");
+          for (int i = 2 * warp; i < NP; i += 2 * NW) {
+            V2 f3[2], dz3[2 * T], o[2 * T];
+            silu_both2(ld2(sZ3 + (l * NP + i) * H, lane), f3[0]);
+            silu_both2(ld2(sZ3 + (l * NP + i + 1) * H, lane), f3[1]);
+            matvec<2 * T>(sW + pk::M, sDAgg + i * T * H, lane, dz3);
             if (!first) {
-              matvec<T>(sW, sDH + i * T * H, lane, o);
+              matvec<2 * T>(sW, sDH + i * T * H, lane, o);
 #pragma unroll
-              for (int t = 0; t < T; ++t) { dz3[t].a += o[t].a; dz3[t].b += o[t].b; }
+              for (int t = 0; t < 2 * T; ++t) { dz3[t].a += o[t].a; dz3[t].b += o[t].b; }
             }
             __syncwarp();
 #pragma unroll
-            for (int t = 0; t < T; ++t) st2(sDAgg + (i * T + t) * H, lane, V2{f3.a * dz3[t].a, f3.b * dz3[t].b});  // own rows
+            for (int t = 0; t < 2 * T; ++t)
+              st2(sDAgg + (i * T + t) * H, lane, V2{f3[t / T].a * dz3[t].a, f3[t / T].b * dz3[t].b});  // own rows
             __syncwarp();
-            matvec<T>(sW + 2 * pk::M, sDAgg + i * T * H, lane, o);
+            matvec<2 * T>(sW + 2 * pk::M, sDAgg + i * T * H, lane, o);
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
+            for (int t = 0; t < 2 * T; ++t) {
               V2 dh = first ? V2{0.f, 0.f} : ld2(sDH + (i * T + t) * H, lane);
               st2(sDH + (i * T + t) * H, lane, V2{dh.a + o[t].a, dh.b + o[t].b});
             }
