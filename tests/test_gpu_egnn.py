@@ -149,6 +149,51 @@ def test_full_size_properties(n, mode):
     assert_close(d1[:k], div_ref, "div slice")
 
 
+def test_bench_size_properties_lj55():
+    """BASELINE.json's own size (LJ-55, 262 144 particles per GPU) through size-independent properties of the default engine:
+    run-to-run determinism, independence of a particle's result from its position in the batch (first / last rows recomputed
+    in a small batch, bit-exact), rotation invariance of the energy and of the divergence and rotation covariance of the score
+    and of the energy gradient (E(3) equivariance of the EGNN), and a slice against the fp64 oracle."""
+    from pita_b200 import ops
+    from pita_b200.egnn_temp_conditioned import pack_state_dict
+    n, B = 55, 1 << 18
+    sd = O.random_egnn_state(seed=11, dtype=torch.float64, coord_gain=0.3)
+    w = pack_state_dict(sd, 32, 3, "cuda")
+    sched = O.EDMSchedule(0.05)
+    gen = torch.Generator().manual_seed(0)
+    base = O.centre(O.md_shaped_coords(4096, n, seed=5) * 1.5, n)
+    x = (base.repeat(B // 4096, 1) * (1 + 0.05 * torch.rand(B, 1, generator=gen))).float().cuda()
+    ht = torch.full((B,), float(sched.h(torch.tensor(0.45, dtype=torch.float64))), device="cuda")
+    s1, d1 = ops.egnn_score_div(w, 32, 3, n, ht, x, 0.8)
+    e1, g1, h1 = ops.egnn_energy(w, 32, 3, n, ht, x, 0.8)
+    assert all(bool(torch.isfinite(v).all()) for v in (s1, d1, e1, g1, h1))
+    s2, d2 = ops.egnn_score_div(w, 32, 3, n, ht, x, 0.8)
+    assert torch.equal(s1, s2) and torch.equal(d1, d2), "not deterministic at bench size"
+    for sl in (slice(0, 64), slice(B - 77, B)):
+        ss, ds = ops.egnn_score_div(w, 32, 3, n, ht[sl], x[sl].contiguous(), 0.8)
+        assert torch.equal(ss, s1[sl]) and torch.equal(ds, d1[sl]), "result depends on the position in the batch"
+        es, gs, hs = ops.egnn_energy(w, 32, 3, n, ht[sl], x[sl].contiguous(), 0.8)
+        assert torch.equal(es, e1[sl]) and torch.equal(gs, g1[sl]) and torch.equal(hs, h1[sl])
+    # a proper rotation (about an arbitrary axis), applied to every atom
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=gen, dtype=torch.float64))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    R = q.float().cuda()
+    sub = slice(0, B, 37)   # a strided subset is enough for the comparison, the kernels ran on everything above
+    xr = (x[sub].reshape(-1, n, 3) @ R.T).reshape(-1, 3 * n).contiguous()
+    sr, dr = ops.egnn_score_div(w, 32, 3, n, ht[sub], xr, 0.8)
+    er, gr, hr = ops.egnn_energy(w, 32, 3, n, ht[sub], xr, 0.8)
+    rot = lambda v: (v.reshape(-1, n, 3) @ R.T).reshape(-1, 3 * n)  # noqa: E731
+    assert_close(dr, d1[sub], "divergence is rotation invariant", rtol=2e-4)
+    assert_close(er, e1[sub], "energy is rotation invariant", rtol=2e-4)
+    assert_close(hr, h1[sub], "dE/dh is rotation invariant", rtol=2e-4)
+    assert_close(sr, rot(s1[sub]), "score is rotation covariant", rtol=2e-4)
+    assert_close(gr, rot(g1[sub]), "grad E is rotation covariant", rtol=2e-4)
+    k = 2
+    div_ref = O.exact_divergence(lambda hh, xx: O.model_score(sd, hh, xx, 0.8, n), ht[:k].double().cpu(), x[:k].double().cpu())
+    assert_close(d1[:k], div_ref, "div slice vs the fp64 oracle")
+
+
 @pytest.mark.parametrize("n,B", [(13, 20), (55, 5)])
 def test_bilinear_engine_tables_vs_oracle(n, B):
     """Every per-pair table the bilinear engine's phase A writes, its direct part and phase B's per-tile partial sums
