@@ -50,6 +50,13 @@ int pita_lj_energy_force(const float *x, int64_t B, int n, float temperature, fl
  * the egnn_temp.yaml configuration: hidden 32, SiLU, recurrent, tanh, attention, agg=sum, time and
  * temperature conditioning.  Weights are passed as ONE packed fp32 device buffer whose layout is
  * produced by pita_egnn_pack_floats / pita_b200.egnn_temp_conditioned.pack_state_dict (host side).
+ *
+ * The same three entry points (forward, energy, score_div) also serve the alanine-dipeptide denoiser
+ * EGNN_dynamics_AD2_cat (models/components/egnn_dynamics_ad2_cat.py:11-218 over models/components/egnn.py:108-184):
+ * (hidden, layers, n) = (64, 5, 22) with condition_beta, node features one_hot(atom type, 21 columns) ++ t ++ beta;
+ * weight buffer from pita_b200.egnn_dynamics_ad2_cat.pack_state_dict_ad2 (pita_egnn_pack_floats(64, 5) floats).  That
+ * network runs on the fp32 CUDA cores in every `mode` and needs no workspace.  Any other (hidden, layers, n) returns
+ * PITA_EUNSUP.
  * ------------------------------------------------------------------------------------------------ */
 /* number of floats in a packed weight buffer for `layers` E_GCL blocks of width `hidden` */
 int64_t pita_egnn_pack_floats(int hidden, int layers);
@@ -76,7 +83,7 @@ int pita_egnn_energy_laplacian(const float *wpack, int hidden, int layers, int n
  * score[B][3n], div[B] (NULL to skip the divergence).
  * mode selects how the dense tangent contraction of the divergence is evaluated:
  *   PITA_DIV_FP32   fp32 CUDA cores (reference-accurate, slowest)
- *   PITA_DIV_3XTF32 tcgen05 tensor cores, error-compensated TF32 (the default): weights and primal operand rows split
+ *   PITA_DIV_3XTF32 tcgen05 tensor cores, error-compensated TF32 (the round-1 default): weights and primal operand rows split
  *                   hi + lo (3xTF32), tangent operand rows rounded once against the exactly split weights; measured
  *                   divergence error <= 1.2e-5 relative, score error as fp32
  *   PITA_DIV_TF32   tcgen05 tensor cores, plain TF32 for the divergence (looser, stated bound 5e-2 relative on the
