@@ -16,7 +16,7 @@ class ScoreNet(nn.Module):
         super().__init__()
         self.model = model
         self.precondition_beta = precondition_beta
-        self.div_mode = div_mode  # None -> PITA_DIV_MODE / "3xtf32"; "fp32" | "3xtf32" | "tf32"
+        self.div_mode = div_mode  # None -> PITA_DIV_MODE / "bilinear"; "bilinear" | "fp32" | "3xtf32" | "tf32"
 
     def score_and_divergence(self, h_t, x_t, beta, need_div=True):
         m = self.model

@@ -149,6 +149,35 @@ def test_full_size_properties(n, mode):
     assert_close(d1[:k], div_ref, "div slice")
 
 
+@pytest.mark.parametrize("precond", [False, True])
+def test_denoisers_vs_oracle(precond):
+    """ScoreNet.denoiser (score_net.py:21-43, with and without precondition_beta, return_score) and EnergyNet.denoiser /
+    denoiser_and_energy (energy_net.py:64-79: x - h grad U, dU/dh, U) against the fp64 oracle (the inference half)."""
+    from pita_b200.energy_net import EnergyNet
+    from pita_b200.score_net import ScoreNet
+    n, B = 13, 23
+    sd = O.random_egnn_state(seed=5, dtype=torch.float64, coord_gain=0.3)
+    net = make_net(n, sd)
+    x = O.centre(O.md_shaped_coords(B, n, seed=9, dtype=torch.float64) * 1.3, n)
+    ht = O.EDMSchedule(0.05).h(torch.linspace(0.3, 0.7, B, dtype=torch.float64))
+    beta = 0.8
+    s_ref = O.model_score(sd, ht, x, beta, n, precondition_beta=precond)
+    d_ref = x + ht[:, None] * s_ref
+    d_theta, score = ScoreNet(net, precondition_beta=precond).denoiser(ht.float().cuda(), x.float().cuda(), torch.tensor(beta, device="cuda"),
+                                                                       return_score=True)
+    assert_close(score, s_ref, "ScoreNet.denoiser score")
+    assert_close(d_theta, d_ref, "ScoreNet.denoiser D_theta")
+    hr, xr = ht.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    u = O.model_energy(sd, hr, xr, beta, n, precondition_beta=precond)
+    gx, gh = torch.autograd.grad(u.sum(), (xr, hr))
+    en = EnergyNet(net, precondition_beta=precond)
+    den, du_dh, U = en.denoiser_and_energy(ht.float().cuda(), x.float().cuda(), torch.tensor(beta, device="cuda"))
+    assert_close(U, u.detach(), "EnergyNet.denoiser_and_energy U")
+    assert_close(du_dh, gh, "EnergyNet.denoiser_and_energy dU/dh", rtol=2e-4)
+    assert_close(den, x - ht[:, None] * gx, "EnergyNet.denoiser_and_energy denoiser")
+    assert_close(en.denoiser(ht.float().cuda(), x.float().cuda(), torch.tensor(beta, device="cuda")), x - ht[:, None] * gx, "EnergyNet.denoiser")
+
+
 def test_bench_size_properties_lj55():
     """BASELINE.json's own size (LJ-55, 262 144 particles per GPU) through size-independent properties of the default engine:
     run-to-run determinism, independence of a particle's result from its position in the batch (first / last rows recomputed
