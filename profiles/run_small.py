@@ -1,5 +1,5 @@
 """Launches every kernel of the library once on a SMALL batch (for compute-sanitizer memcheck / racecheck and for NVTX-ranged
-captures; not a benchmark):  python profiles/run_small.py [lj|egnn13|egnn55|ad2|loop|all]"""
+captures; not a benchmark):  python profiles/run_small.py [lj|egnn13|egnn55|ad2|lap|loop|all]"""
 import os
 import sys
 
@@ -49,6 +49,15 @@ if which in ("ad2", "all"):
     ops.egnn_forward(w, 64, 5, 22, ht, x, 0.9)
     ops.egnn_energy(w, 64, 5, 22, ht, x, 0.9)
     ops.egnn_score_div(w, 64, 5, 22, ht, x, 0.9)
+if which == "lap13":   # one particle: the racecheck build of the 3n-pass kernel is slow
+    net = lj_net(13)
+    x = ops.remove_mean(torch.randn(1, 39, device="cuda") * 2.0, 13)
+    ops.egnn_energy_laplacian(net.packed_weights("cuda"), 32, 3, 13, torch.full((1,), 3.0, device="cuda"), x, 0.8)
+if which in ("lap", "all"):
+    for n, B in ((13, 6), (55, 2)):
+        net = lj_net(n)
+        x = ops.remove_mean(torch.randn(B, 3 * n, device="cuda") * 2.0, n)
+        ops.egnn_energy_laplacian(net.packed_weights("cuda"), 32, 3, n, torch.full((B,), 3.0, device="cuda"), x, 0.8)
 if which in ("loop", "all"):
     n, B = 13, 300
     x, e, g, dh, s, d = egnn(n, B)
