@@ -39,8 +39,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: LJ-55, 256k-4M particles sharded across 1/2/4/8 B200
     "lj55": dict(n=55, particles=1 << 18, chunk=512, sigma_min=0.05, label="LJ-55 annealed FK sampling, 256k particles/GPU (BASELINE configs[2])"),
     # SURVEY §8 row a8': the alanine-dipeptide denoiser (EGNN_dynamics_AD2_cat, 22 atoms, hidden 64, 5 layers) in the same loop;
-    # the molecular target energy (OpenMM) is out of scope and is not on the pin_energy=False path
-    "aldp22": dict(n=22, particles=1 << 14, chunk=512, sigma_min=0.05, hidden=64, layers=5,
+    # the molecular target energy (OpenMM) is out of scope and is not on the pin_energy=False path; chunk = inference_batch_size
+    # of configs/experiment/aldp.yaml:27
+    "aldp22": dict(n=22, particles=1 << 14, chunk=2048, sigma_min=0.05, hidden=64, layers=5,
                    label="ALDP-22 annealed FK sampling (EGNN_dynamics_AD2_cat 64x5), 16k particles/GPU"),
 }
 CPU_SAMPLE = {13: (512, 64), 22: (96, 24), 55: (16, 8)}            # (particles per step, inference chunk) of the host legs
